@@ -1,0 +1,227 @@
+"""Thin Python binding of the C ABI in include/icspcuda.h (used by tests/ and bench.py).
+
+The reference is compiled C++ with no plugin API, so the *product* host side is C++ (icspcodec_b200/host:
+icspenc / icspdec).  This module only marshals numpy arrays into the same extern "C" calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+class IcspError(RuntimeError):
+    pass
+
+
+@dataclass
+class EncResult:
+    levels: np.ndarray   # int16 [n][nmb][6][64]
+    acflag: np.ndarray   # uint8 [n][nmb][6]
+    mpm: np.ndarray      # uint8 [n][nmb][4]
+    ipm: np.ndarray      # uint8 [n][nmb][4]
+    mvd: np.ndarray      # int16 [n][nmb][2]
+    mv: np.ndarray       # int16 [n][nmb][2]
+    minsad: np.ndarray   # int32 [n][nmb]
+    recon: np.ndarray    # uint8 [n][fb]
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'd memory (kept alive by this object)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = _lib.load()
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = self._lib.icsp_host_alloc(max(nbytes, 1))
+        if not self._p:
+            raise IcspError("icsp_host_alloc failed")
+        buf = (C.c_char * max(nbytes, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_p", None):
+                self.array = None
+                self._lib.icsp_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+class IcspCuda:
+    """One context = one GPU + one stream + device SoA buffers for up to `max_frames` frames."""
+
+    def __init__(self, width: int = 352, height: int = 288, max_frames: int = 64, device: int = 0):
+        self.lib = _lib.load()
+        self.w, self.h, self.cap = width, height, max_frames
+        self.nmb = (width // 16) * (height // 16)
+        self.fb = width * height * 3 // 2
+        h = C.c_void_p()
+        rc = self.lib.icsp_create(C.byref(h), device, width, height, max_frames)
+        if rc != 0:
+            raise IcspError(f"icsp_create failed ({rc}): {self.lib.icsp_last_error(None).decode()}")
+        self.h_ctx = h
+
+    def close(self):
+        if getattr(self, "h_ctx", None):
+            self.lib.icsp_destroy(self.h_ctx)
+            self.h_ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc: int, what: str):
+        if rc != 0:
+            raise IcspError(f"{what} failed ({rc}): {self.lib.icsp_last_error(self.h_ctx).decode()}")
+
+    # ---- encoder -----------------------------------------------------------------------------------
+    def alloc_result(self, n: int, pinned: bool = False) -> EncResult:
+        shapes = dict(levels=((n, self.nmb, 6, 64), np.int16), acflag=((n, self.nmb, 6), np.uint8),
+                      mpm=((n, self.nmb, 4), np.uint8), ipm=((n, self.nmb, 4), np.uint8),
+                      mvd=((n, self.nmb, 2), np.int16), mv=((n, self.nmb, 2), np.int16),
+                      minsad=((n, self.nmb), np.int32), recon=((n, self.fb), np.uint8))
+        if pinned:
+            self._pins = getattr(self, "_pins", [])
+            out = {}
+            for k, (sh, dt) in shapes.items():
+                pa = PinnedArray(sh, dt)
+                self._pins.append(pa)
+                out[k] = pa.array
+            return EncResult(**out)
+        return EncResult(**{k: np.zeros(sh, dt) for k, (sh, dt) in shapes.items()})
+
+    @staticmethod
+    def _enc_out(res: EncResult, fields=None) -> _lib.EncOut:
+        o = _lib.EncOut()
+        for name in ("levels", "acflag", "mpm", "ipm", "mvd", "mv", "minsad", "recon"):
+            want = fields is None or name in fields
+            setattr(o, name, _ptr(getattr(res, name)) if want else None)
+        return o
+
+    def encode_gops(self, frames: np.ndarray, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int,
+                    out: EncResult | None = None, fields=None) -> EncResult:
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = n_gops * gop_len
+        if frames.size != n * self.fb:
+            raise IcspError(f"expected {n} frames of {self.fb} bytes")
+        res = out or self.alloc_result(n)
+        o = self._enc_out(res, fields)
+        self._chk(self.lib.icsp_encode_gops(self.h_ctx, _ptr(frames), n_gops, gop_len, qp_dc, qp_ac, C.byref(o)), "icsp_encode_gops")
+        return res
+
+    def encode_sequence(self, frames: np.ndarray, qp_dc: int, qp_ac: int, intra_period: int) -> EncResult:
+        """Frame loop of single_thread_encoding (ENC:217-245): I-frame iff n % intra_period == 0 (0 = all intra).
+        Full GOPs go out as one batch, the tail (nframes % intra_period) as a second, shorter GOP."""
+        frames = np.ascontiguousarray(frames, np.uint8).reshape(-1, self.fb)
+        n = frames.shape[0]
+        ip = 1 if intra_period == 0 else intra_period
+        res = self.alloc_result(n)
+        full = n // ip
+        parts = []
+        if full:
+            parts.append((0, full, ip))
+        if n - full * ip:
+            parts.append((full * ip, 1, n - full * ip))
+        for start, ng, gl in parts:
+            cnt = ng * gl
+            sub = EncResult(**{k: getattr(res, k)[start:start + cnt] for k in res.__dataclass_fields__})
+            self.encode_gops(frames[start:start + cnt], ng, gl, qp_dc, qp_ac, out=sub)
+        return res
+
+    def upload(self, frames: np.ndarray):
+        n = frames.size // self.fb
+        self._chk(self.lib.icsp_enc_upload(self.h_ctx, _ptr(frames), n), "icsp_enc_upload")
+
+    def run(self, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int):
+        self._chk(self.lib.icsp_enc_run(self.h_ctx, n_gops, gop_len, qp_dc, qp_ac), "icsp_enc_run")
+
+    def download(self, n: int, res: EncResult, fields=None):
+        o = self._enc_out(res, fields)
+        self._chk(self.lib.icsp_enc_download(self.h_ctx, n, C.byref(o)), "icsp_enc_download")
+
+    def sync(self):
+        self._chk(self.lib.icsp_sync(self.h_ctx), "icsp_sync")
+
+    # ---- decoder -----------------------------------------------------------------------------------
+    def decode_gops(self, levels, mpm, ipm, mvd, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int) -> np.ndarray:
+        n = n_gops * gop_len
+        levels = np.ascontiguousarray(levels, np.int16)
+        mpm = np.ascontiguousarray(mpm, np.uint8)
+        ipm = np.ascontiguousarray(ipm, np.uint8)
+        mvd = np.ascontiguousarray(mvd, np.int16)
+        assert levels.size == n * self.nmb * 384
+        din = _lib.DecIn(_ptr(levels), _ptr(mpm), _ptr(ipm), _ptr(mvd))
+        out = np.zeros((n, self.fb), np.uint8)
+        self._chk(self.lib.icsp_decode_gops(self.h_ctx, C.byref(din), n_gops, gop_len, qp_dc, qp_ac, _ptr(out)), "icsp_decode_gops")
+        return out
+
+    def decode_sequence(self, levels, mpm, ipm, mvd, qp_dc: int, qp_ac: int, intra_period: int) -> np.ndarray:
+        """Frame loop of IcspCodec::decoding (DEC.h:290-313): intra iff intra_period == 1 or n % intra_period == 0."""
+        n = levels.shape[0]
+        ip = intra_period
+        outs = []
+        full = n // ip
+        if full:
+            c = full * ip
+            outs.append(self.decode_gops(levels[:c], mpm[:c], ipm[:c], mvd[:c], full, ip, qp_dc, qp_ac))
+        if n - full * ip:
+            s = full * ip
+            outs.append(self.decode_gops(levels[s:], mpm[s:], ipm[s:], mvd[s:], 1, n - s, qp_dc, qp_ac))
+        return np.concatenate(outs, axis=0)
+
+    # ---- shims -------------------------------------------------------------------------------------
+    def me_sad(self, cur_y: np.ndarray, ref_y: np.ndarray):
+        cur_y = np.ascontiguousarray(cur_y, np.uint8).reshape(-1, self.w * self.h)
+        ref_y = np.ascontiguousarray(ref_y, np.uint8).reshape(-1, self.w * self.h)
+        n = cur_y.shape[0]
+        mv = np.zeros((n, self.nmb, 2), np.int16)
+        sad = np.zeros((n, self.nmb), np.int32)
+        self._chk(self.lib.icsp_me_sad(self.h_ctx, _ptr(cur_y), _ptr(ref_y), n, _ptr(mv), _ptr(sad)), "icsp_me_sad")
+        return mv, sad
+
+    def dct8x8(self, blocks: np.ndarray) -> np.ndarray:
+        blocks = np.ascontiguousarray(blocks, np.int32).reshape(-1, 64)
+        out = np.zeros(blocks.shape, np.float64)
+        self._chk(self.lib.icsp_dct8x8(self.h_ctx, _ptr(blocks), blocks.shape[0], _ptr(out)), "icsp_dct8x8")
+        return out
+
+    def idct8x8(self, blocks: np.ndarray, table: int = 0) -> np.ndarray:
+        blocks = np.ascontiguousarray(blocks, np.int32).reshape(-1, 64)
+        out = np.zeros(blocks.shape, np.float64)
+        self._chk(self.lib.icsp_idct8x8(self.h_ctx, _ptr(blocks), blocks.shape[0], table, _ptr(out)), "icsp_idct8x8")
+        return out
+
+    # ---- instrumentation ---------------------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        self._chk(self.lib.icsp_set_profiling(self.h_ctx, int(on)), "icsp_set_profiling")
+
+    def reset_stats(self):
+        self._chk(self.lib.icsp_reset_stats(self.h_ctx), "icsp_reset_stats")
+
+    def stats(self) -> dict:
+        arr = (_lib.KernelStat * _lib.MAX_KERNELS)()
+        n = self.lib.icsp_get_stats(self.h_ctx, arr, _lib.MAX_KERNELS)
+        return {arr[i].name.decode(): dict(launches=int(arr[i].launches), total_ms=float(arr[i].total_ms)) for i in range(max(n, 0))}
+
+    def launch_count(self) -> int:
+        return int(self.lib.icsp_launch_count(self.h_ctx))
+
+    def event_record(self, slot: int):
+        self._chk(self.lib.icsp_event_record(self.h_ctx, slot), "icsp_event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.icsp_event_elapsed_ms(self.h_ctx, a, b, C.byref(ms)), "icsp_event_elapsed_ms")
+        return float(ms.value)

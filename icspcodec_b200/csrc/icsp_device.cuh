@@ -1,0 +1,208 @@
+// Device-side building blocks shared by every kernel of libicspcuda (sm_100a).
+//
+// Numerical contract: IEEE binary64, one rounding per multiply and per add
+// exactly where the reference (compiled without FMA) rounds.  Every FP64 operation below is an explicit
+// __dmul_rn/__dadd_rn/__dsub_rn (never contracted by the compiler); __fma_rn appears only where the
+// product is exactly representable (int x float-widened constant), so fused == unfused bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace icsp {
+
+struct Geom {
+    int w, h;      // luma size
+    int mbw, mbh;  // macroblock grid
+    int nmb;
+    int cw, ch;    // chroma size
+    int bw, bh;    // luma 8x8 grid
+    int fb;        // bytes per I420 frame
+};
+
+// costable[u][x]: table 0 = encoder (binary32 literals widened, ENC.h:190-198), 1 = decoder (binary64, DEC.h:19-27)
+__constant__ double c_T[2][8][8];
+__constant__ double c_irt2;                 // 1.0/sqrt(2.0)  (ENC.h:199)
+__constant__ unsigned char c_ZZ[64];        // zig-zag position k -> raster index (ENC:3031-3094)
+__constant__ unsigned char c_IZ[64];        // raster index -> zig-zag position
+__constant__ signed char c_cand[8][64][2];  // spiral visiting order per carried start state: (dx,dy) (ENC:2101-2143)
+__constant__ unsigned char c_next[8][65];   // start state, moves made -> state handed to the next macroblock
+
+__device__ __forceinline__ int med3(int a, int b, int c)
+{  // ENC:3677-3679
+    if (a > b && a > c) return b > c ? b : c;
+    if (b > a && b > c) return a > c ? a : c;
+    return a > b ? a : b;
+}
+__device__ __forceinline__ int clip255(int v) { return min(255, max(0, v)); }
+
+// R1 (getPaddingImage, ENC:2227-2269): padded(y,x) = src(clamp) except the LAST padded row/column, which stay 0.
+__device__ __forceinline__ int ref_px(const uint8_t* __restrict__ P, int w, int h, int pad, int y, int x)
+{
+    if (y == h + 2 * pad - 1 || x == w + 2 * pad - 1) return 0;
+    int yy = min(max(y - pad, 0), h - 1), xx = min(max(x - pad, 0), w - 1);
+    return P[yy * w + xx];
+}
+
+// 8 consecutive prediction pixels of one row, starting at padded coordinate (y, x0).
+__device__ __forceinline__ void ref_row8(const uint8_t* __restrict__ P, int w, int h, int pad, int y, int x0, int out[8])
+{
+    const int ux = x0 - pad, uy = y - pad;
+    if (uy >= 0 && uy < h && ux >= 0 && ux + 7 < w) {  // interior: no clamping, no zero row/col
+        const uint8_t* p = P + uy * w + ux;
+        const uintptr_t a = (uintptr_t)p;
+        const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = sh ? __ldg(q + 2) : 0u;
+        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            out[i] = (lo >> (8 * i)) & 255;
+            out[4 + i] = (hi >> (8 * i)) & 255;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = ref_px(P, w, h, pad, y, x0 + i);
+    }
+}
+
+// ---- A.5 DC predictors on the 8x8 grid of one plane (dc = reconstructed DCs, row-major [bh][bw]) ----
+__device__ __forceinline__ int dc_pred_luma(const int* dc, int bw, int bx, int by)
+{  // ENC:3643-3990 reduced to geometry
+    if (bx == 0 && by == 0) return 1024;
+    if (by == 0) return dc[bx - 1];
+    if (bx == 0) return dc[(by - 1) * bw];
+    const int L = dc[by * bw + bx - 1], U = dc[(by - 1) * bw + bx];
+    if ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1)) return med3(L, U, dc[(by - 1) * bw + bx + 1]);
+    return med3(L, dc[(by - 1) * bw + bx - 1], U);
+}
+__device__ __forceinline__ int dc_pred_chroma(const int* dc, int bw, int bx, int by)
+{  // ENC:4482-4513
+    if (bx == 0 && by == 0) return 1024;
+    if (by == 0) return dc[bx - 1];
+    if (bx == 0) return dc[(by - 1) * bw];
+    const int L = dc[by * bw + bx - 1], U = dc[(by - 1) * bw + bx];
+    if (bx == bw - 1) return med3(L, dc[(by - 1) * bw + bx - 1], U);
+    return med3(L, U, dc[(by - 1) * bw + bx + 1]);
+}
+
+// ---- quantiser (A.4) ----------------------------------------------------------------------------
+// luma ENC:2780  (int)(D+0.5)/Q ; chroma ENC:4642  (int)floor(D+0.5)/Q ; both divisions truncate toward zero
+__device__ __forceinline__ int quant(double D, int Q, bool chroma)
+{
+    const double x = __dadd_rn(D, 0.5);
+    const int r = chroma ? __double2int_rd(x) : __double2int_rz(x);
+    return r / Q;
+}
+
+// ---- 8x8 transforms, one 8-lane group per block --------------------------------------------------
+// Stage 1 of the forward DCT (ENC:2709-2718) for one row: t[u] = sum_x E[x]*T[u][x].
+// Every term and every partial sum is exactly representable (|E|<=255, 24-bit constants, < 38 bits), so
+// the even/odd factorisation below returns the reference's value bit for bit.
+__device__ __forceinline__ void fdct_row(const int e[8], double t[8])
+{
+    const double a = c_T[0][1][0], b = c_T[0][1][1], c = c_T[0][1][2], d = c_T[0][1][3];
+    const double E = c_T[0][2][0], F = c_T[0][2][1], G = c_T[0][4][0];
+    const int s0 = e[0] + e[7], s1 = e[1] + e[6], s2 = e[2] + e[5], s3 = e[3] + e[4];
+    const double d0 = (double)(e[0] - e[7]), d1 = (double)(e[1] - e[6]), d2 = (double)(e[2] - e[5]), d3 = (double)(e[3] - e[4]);
+    const double p03 = (double)(s0 - s3), p12 = (double)(s1 - s2);
+    t[0] = (double)(s0 + s1 + s2 + s3);
+    t[4] = __dmul_rn(G, (double)(s0 - s1 - s2 + s3));
+    t[2] = __fma_rn(F, p12, __dmul_rn(E, p03));
+    t[6] = __fma_rn(-E, p12, __dmul_rn(F, p03));
+    t[1] = __fma_rn(d, d3, __fma_rn(c, d2, __fma_rn(b, d1, __dmul_rn(a, d0))));
+    t[3] = __fma_rn(-c, d3, __fma_rn(-a, d2, __fma_rn(-d, d1, __dmul_rn(b, d0))));
+    t[5] = __fma_rn(b, d3, __fma_rn(d, d2, __fma_rn(-a, d1, __dmul_rn(c, d0))));
+    t[7] = __fma_rn(-a, d3, __fma_rn(b, d2, __fma_rn(-c, d1, __dmul_rn(d, d0))));
+}
+// Stage 2 (ENC:2720-2729) for one column u: D[v] = sum_y fl(t[y]*T[v][y]), y ascending, rounded per op;
+// then the irt2 / 0.25 scaling of ENC:2732-2744 (element [0][0] is scaled by irt2 twice, in sequence).
+__device__ __forceinline__ void fdct_col(const double t[8], int u, double D[8])
+{
+    double s = t[0];
+#pragma unroll
+    for (int y = 1; y < 8; y++) s = __dadd_rn(s, t[y]);  // T[0][y] == 1.0
+    D[0] = s;
+#pragma unroll
+    for (int v = 1; v < 8; v++) {
+        double acc = __dmul_rn(t[0], c_T[0][v][0]);
+#pragma unroll
+        for (int y = 1; y < 8; y++) acc = __dadd_rn(acc, __dmul_rn(t[y], c_T[0][v][y]));
+        D[v] = acc;
+    }
+    D[0] = __dmul_rn(D[0], c_irt2);
+    if (u == 0) {
+#pragma unroll
+        for (int v = 0; v < 8; v++) D[v] = __dmul_rn(D[v], c_irt2);
+    }
+#pragma unroll
+    for (int v = 0; v < 8; v++) D[v] = __dmul_rn(D[v], 0.25);
+}
+
+// Stage 1 of the IDCT (ENC:2858-2867) for one row y: t[x] = sum_u (C[u]*Q[u])*T[u][x].
+// TAB==0: Q[u]*T[u][x] is exact (int x float-widened constant) so an FMA equals mul-then-add;
+// TAB==1 (decoder, binary64 table): the product is inexact and must be rounded separately.
+template <int TAB>
+__device__ __forceinline__ void idct_row(const int q[8], double t[8])
+{
+    const double a0 = __dmul_rn(c_irt2, (double)q[0]);
+    double qd[8];
+#pragma unroll
+    for (int u = 1; u < 8; u++) qd[u] = (double)q[u];
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        double s = a0;
+#pragma unroll
+        for (int u = 1; u < 8; u++) {
+            if (TAB == 0) s = __fma_rn(qd[u], c_T[0][u][x], s);
+            else s = __dadd_rn(s, __dmul_rn(qd[u], c_T[1][u][x]));
+        }
+        t[x] = s;
+    }
+}
+// Stage 2 (ENC:2869-2878) for one column x: R[y] = sum_v fl((C[v]*t[v])*T[v][y]), then *0.25 (ENC:2885-2891).
+// T[v][7-y] == (-1)^v T[v][y] exactly, so each rounded product serves two outputs.
+template <int TAB>
+__device__ __forceinline__ void idct_col(const double t[8], double R[8])
+{
+    const double a0 = __dmul_rn(c_irt2, t[0]);
+    double lo[4], hi[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) lo[y] = hi[y] = a0;
+#pragma unroll
+    for (int v = 1; v < 8; v++) {
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const double p = __dmul_rn(t[v], c_T[TAB][v][y]);
+            lo[y] = __dadd_rn(lo[y], p);
+            hi[y] = (v & 1) ? __dsub_rn(hi[y], p) : __dadd_rn(hi[y], p);
+        }
+    }
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        R[y] = __dmul_rn(lo[y], 0.25);
+        R[7 - y] = __dmul_rn(hi[y], 0.25);
+    }
+}
+
+// 8x8 transposition inside one 8-lane group through a padded shared tile (pitch 9).
+template <typename T>
+__device__ __forceinline__ void group_transpose(T v[8], T* tile, int r)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) tile[r * 9 + k] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = tile[k * 9 + r];
+    __syncwarp();
+}
+
+// sum over the 8 lanes of a group (groups are aligned to 8 lanes inside a warp)
+__device__ __forceinline__ int group_sum(int v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+}  // namespace icsp

@@ -1,0 +1,667 @@
+// Kernels of libicspcuda (sm_100a).  One launch processes the same intra-GOP frame index t of EVERY GOP in the
+// batch (blockIdx.y = GOP), because closed GOPs share no state (README.md:152) while frames inside a GOP are
+// strictly sequential.  Frame index of GOP g at step t: f = g*gop_len + t.
+#pragma once
+#include "icsp_device.cuh"
+
+namespace icsp {
+
+struct FramePtrs {
+    const uint8_t* cur;  // [F][fb] input frames
+    uint8_t* rec;        // [F][fb] reconstruction
+    int16_t* levels;     // [F][nmb][6][64]
+    uint8_t* acflag;     // [F][nmb][6]
+    uint8_t* mpm;        // [F][nmb][4]
+    uint8_t* ipm;        // [F][nmb][4]
+    int16_t* mvd;        // [F][nmb][2]
+    int16_t* mv;         // [F][nmb][2]
+    int32_t* minsad;     // [F][nmb]
+    double* dcraw;       // [G][6*nmb] scaled forward-DCT DC, plane-raster order: Y[bh][bw], Cb[mbh][mbw], Cr
+    int32_t* dcrec;      // [G][6*nmb] reconstructed DC, same order
+    uint8_t* mestate;    // [G][nmb]  spiral start state per macroblock
+    uint8_t* memoves;    // [G][nmb]  moves made by the search (64 = no early break)
+    uint32_t* meflag;    // [G]       number of macroblocks of the frame whose search broke early
+    unsigned long long* mezero;  // [G][nmb][8] zero-SAD masks per start state (exact fallback only)
+};
+
+struct Step {
+    int gop_len, t;  // f = g*gop_len + t
+    int qdc, qac;
+    int intra;       // 1: intra frame (transform kernels touch chroma only; luma is the wavefront kernel)
+};
+
+// item -> (mb, k, plane geometry)
+struct BlockId {
+    int mb, k, plane;  // plane 0 Y, 1 Cb, 2 Cr
+    int bx, by;        // position in the plane's 8x8 grid
+    int pw, ph;        // plane size
+    int poff;          // plane offset inside a frame
+    int dcidx;         // index into dcraw/dcrec (plane-raster order)
+};
+__device__ __forceinline__ BlockId block_id(const Geom& g, int item, int intra)
+{
+    BlockId b;
+    if (intra) { b.mb = item >> 1; b.k = 4 + (item & 1); }
+    else { b.mb = item / 6; b.k = item - b.mb * 6; }
+    const int mbx = b.mb % g.mbw, mby = b.mb / g.mbw;
+    if (b.k < 4) {
+        b.plane = 0; b.bx = 2 * mbx + (b.k & 1); b.by = 2 * mby + (b.k >> 1);
+        b.pw = g.w; b.ph = g.h; b.poff = 0; b.dcidx = b.by * g.bw + b.bx;
+    } else {
+        b.plane = b.k - 3; b.bx = mbx; b.by = mby; b.pw = g.cw; b.ph = g.ch;
+        b.poff = g.w * g.h + (b.k - 4) * g.cw * g.ch;
+        b.dcidx = 4 * g.nmb + (b.k - 4) * g.nmb + b.mb;
+    }
+    return b;
+}
+
+// prediction row r of a block (inter: motion compensated from the previous reconstruction; intra chroma: 0)
+__device__ __forceinline__ void pred_row(const Geom& g, const BlockId& b, const uint8_t* prevf, const int16_t* mvf, int r,
+                                         int intra, int out[8])
+{
+    if (intra) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = 0;
+        return;
+    }
+    const int mx = mvf[2 * b.mb], my = mvf[2 * b.mb + 1];
+    if (b.plane == 0)  // motionCompensation ENC:2185-2186: ref = origin - mv + pad
+        ref_row8(prevf, g.w, g.h, 16, 16 + b.by * 8 + r - my, 16 + b.bx * 8 - mx, out);
+    else               // CmotionCompensation ENC:2538-2539: mv/2 truncates toward zero, pad 8
+        ref_row8(prevf + b.poff, g.cw, g.ch, 8, 8 + b.by * 8 + r - my / 2, 8 + b.bx * 8 - mx / 2, out);
+}
+
+// =====================================================================================================
+// Kernel A: residual + forward DCT + AC quantisation + zig-zag (R3, R5, R7, R8).  8 lanes per 8x8 block.
+// Writes AC levels (DC slot is filled by the DC chain kernel), ACflag and the scaled DC as a double.
+// =====================================================================================================
+constexpr int TR_THREADS = 128;  // 16 blocks per CTA
+__global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtrs p, Step st)
+{
+    __shared__ double s_tile[TR_THREADS / 8][72];
+    __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][64];
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+    const int item = blockIdx.x * (TR_THREADS / 8) + grp;
+    const bool valid = item < nitems;
+    const int gop = blockIdx.y;
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const BlockId b = block_id(g, valid ? item : 0, st.intra);
+    const uint8_t* curf = p.cur + f * g.fb;
+    const uint8_t* prevf = p.rec + (f - (st.intra ? 0 : 1)) * g.fb;
+
+    int e[8], pr[8];
+    {
+        const uint2 cw = *(const uint2*)(curf + b.poff + (size_t)(b.by * 8 + r) * b.pw + b.bx * 8);
+        pred_row(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra, pr);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            e[i] = (int)((cw.x >> (8 * i)) & 255) - pr[i];
+            e[4 + i] = (int)((cw.y >> (8 * i)) & 255) - pr[4 + i];
+        }
+    }
+    double t[8], D[8];
+    fdct_row(e, t);
+    group_transpose(t, s_tile[grp], r);   // lane r now holds column u=r: t[y][r]
+    fdct_col(t, r, D);                     // D[v][u=r]
+
+    const bool chroma = b.k >= 4;
+    int nz = 0;
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+        const int L = quant(D[v], (v == 0 && r == 0) ? st.qdc : st.qac, chroma);
+        s_lv[grp][c_IZ[v * 8 + r]] = (int16_t)L;
+        if (!(v == 0 && r == 0)) nz |= L;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, nz != 0);
+    __syncwarp();
+    if (valid) {
+        int16_t* lv = p.levels + ((f * g.nmb + b.mb) * 6 + b.k) * 64;
+        *(uint4*)(lv + 8 * r) = *(const uint4*)(&s_lv[grp][8 * r]);
+        if (r == 0) {
+            p.acflag[(f * g.nmb + b.mb) * 6 + b.k] = ((bal >> (8 * (grp & 3))) & 0xffu) ? 0 : 1;
+            p.dcraw[(size_t)gop * 6 * g.nmb + b.dcidx] = D[0];
+        }
+    }
+}
+
+// =====================================================================================================
+// Kernel B: DC-DPCM chains (R6) and MV differentials (R4).  One CTA per frame; warp 0 luma, 1 Cb, 2 Cr walk
+// their 8x8 grid in waves w = bx + 2*by (the UR dependency gives slope 2); warp 3 computes mvd = mv - Pm.
+// decode == 0: level = quant(Draw - P), rec = level*Q + P ;  decode == 1: rec = level*Q + P.
+// =====================================================================================================
+__device__ __forceinline__ void mv_predictor(const int16_t* mv, int mbw, int mb, int& px, int& py)
+{  // mvPrediction ENC:2353-2425 (the y-median typo `y1>x3` is the reference's and is kept)
+    const int mbx = mb % mbw;
+    if (mb == 0) { px = 8; py = 8; return; }
+    if (mb < mbw) { px = mv[2 * (mb - 1)]; py = mv[2 * (mb - 1) + 1]; return; }
+    if (mbx == 0) { px = mv[2 * (mb - mbw)]; py = mv[2 * (mb - mbw) + 1]; return; }
+    int a = mb - 1, b, c;
+    if (mbx == mbw - 1) { b = mb - mbw - 1; c = mb - mbw; } else { b = mb - mbw; c = mb - mbw + 1; }
+    const int x1 = mv[2 * a], x2 = mv[2 * b], x3 = mv[2 * c], y1 = mv[2 * a + 1], y2 = mv[2 * b + 1], y3 = mv[2 * c + 1];
+    px = med3(x1, x2, x3);
+    if (y1 > y2 && y1 > y3) py = y2 > y3 ? y2 : y3;
+    else if (y2 > y1 && y2 > y3) py = (y1 > x3) ? y1 : y3;
+    else py = y1 > y2 ? y1 : y2;
+}
+
+__global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step st, int decode)
+{
+    extern __shared__ int s_dc[];  // Y[bh*bw], Cb[nmb], Cr[nmb]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gop = blockIdx.x;
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    if (warp == 3) {
+        if (st.intra || decode) return;
+        const int16_t* mv = p.mv + f * g.nmb * 2;
+        int16_t* mvd = p.mvd + f * g.nmb * 2;
+        for (int mb = lane; mb < g.nmb; mb += 32) {
+            int px, py;
+            mv_predictor(mv, g.mbw, mb, px, py);
+            mvd[2 * mb] = (int16_t)(mv[2 * mb] - px);
+            mvd[2 * mb + 1] = (int16_t)(mv[2 * mb + 1] - py);
+        }
+        return;
+    }
+    if (warp == 0 && st.intra) return;  // intra luma DCs are chained inside the wavefront kernel
+    const bool chroma = warp > 0;
+    const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh;
+    const int base = chroma ? 4 * g.nmb + (warp - 1) * g.nmb : 0;
+    int* dc = s_dc + base;
+    const double* raw = p.dcraw + (size_t)gop * 6 * g.nmb + base;
+    int32_t* rec = p.dcrec + (size_t)gop * 6 * g.nmb + base;
+    int16_t* lvf = p.levels + f * g.nmb * 384;
+    const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
+    for (int wv = 0; wv < nwaves; wv++) {
+        const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
+        for (int by = by_lo + lane; by <= by_hi; by += 32) {
+            const int bx = wv - 2 * by;
+            const int P = chroma ? dc_pred_chroma(dc, bw, bx, by) : dc_pred_luma(dc, bw, bx, by);
+            const int mb = chroma ? by * bw + bx : (by >> 1) * g.mbw + (bx >> 1);
+            const int k = chroma ? 3 + warp : ((by & 1) << 1) | (bx & 1);
+            int16_t* dst = lvf + (mb * 6 + k) * 64;
+            int L;
+            if (decode) L = *dst;
+            else {
+                L = quant(__dsub_rn(raw[by * bw + bx], (double)P), st.qdc, chroma);  // DPCM_DC_block: D -= P (double)
+                *dst = (int16_t)L;
+            }
+            const int v = L * st.qdc + P;  // IQuantization + IDPCM_DC_block
+            dc[by * bw + bx] = v;
+            rec[by * bw + bx] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================
+// Kernel C: dequantisation + IDCT + reconstruction (R9, R10, R13).  8 lanes per block.
+// TAB 0: encoder table (float widened) ; TAB 1: decoder table (binary64).
+// =====================================================================================================
+template <int TAB>
+__global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtrs p, Step st)
+{
+    __shared__ double s_tile[TR_THREADS / 8][72];
+    __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][64];
+    __shared__ __align__(8) uint8_t s_px[TR_THREADS / 8][64];
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+    const int item = blockIdx.x * (TR_THREADS / 8) + grp;
+    const bool valid = item < nitems;
+    const int gop = blockIdx.y;
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const BlockId b = block_id(g, valid ? item : 0, st.intra);
+    const uint8_t* prevf = p.rec + (f - (st.intra ? 0 : 1)) * g.fb;
+
+    const int16_t* lv = p.levels + ((f * g.nmb + b.mb) * 6 + b.k) * 64;
+    *(uint4*)(&s_lv[grp][8 * r]) = *(const uint4*)(lv + 8 * r);
+    int pr[8];
+    pred_row(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra, pr);
+    {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { lo |= (uint32_t)pr[i] << (8 * i); hi |= (uint32_t)pr[4 + i] << (8 * i); }
+        *(uint2*)(&s_px[grp][8 * r]) = make_uint2(lo, hi);
+    }
+    __syncwarp();
+    int q[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][c_IZ[r * 8 + u]] * st.qac;   // IQuantization_block
+    if (r == 0) q[0] = p.dcrec[(size_t)gop * 6 * g.nmb + b.dcidx];                 // level*QstepDC + P
+    double t[8], R[8];
+    idct_row<TAB>(q, t);                  // row y=r
+    group_transpose(t, s_tile[grp], r);   // lane r holds column x=r: t[v][r]
+    idct_col<TAB>(t, R);                  // R[y][x=r]
+    uint8_t out[8];
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        const int pv = s_px[grp][y * 8 + r];
+        int v;
+        if (st.intra) {                      // chroma intra, intraImgReconstruct ENC:1964-1971
+            v = (R[y] > 255.0) ? 255 : __double2int_rz(R[y]);
+            v = max(v, 0);
+        } else if (b.plane == 0) {           // mergeBlock ENC:4812 truncates first, interYReconstruct ENC:2343-2346
+            v = clip255(pv + __double2int_rz(R[y]));
+        } else {                             // interCbCrReconstruct ENC:2605-2607 truncates the double sum
+            v = clip255(__double2int_rz(__dadd_rn((double)pv, R[y])));
+        }
+        out[y] = (uint8_t)v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int y = 0; y < 8; y++) s_px[grp][y * 8 + r] = out[y];
+    __syncwarp();
+    if (valid) {
+        uint8_t* dst = p.rec + f * g.fb + b.poff + (size_t)(b.by * 8 + r) * b.pw + b.bx * 8;
+        *(uint2*)dst = *(const uint2*)(&s_px[grp][8 * r]);
+    }
+}
+
+// =====================================================================================================
+// Intra luma wavefront (R11, R12 + R5-R10 for luma).  One CTA per intra frame; 8 lanes per 8x8 block; the
+// blocks of anti-diagonal wave w = bx + 2*by are independent (they need L, U, UL and, for the DC predictor,
+// UR).  Bottom rows / right columns of reconstructed blocks, DCs and modes live in shared memory.
+// DECODE == 0: mode decision + coding + reconstruction (encoder table);
+// DECODE == 1: mode from (MPM, bit) + reconstruction with the decoder's binary64 table.
+// =====================================================================================================
+constexpr int IW_THREADS = 192;  // 24 block slots per wave step
+struct IntraSmem {
+    uint8_t* bot;    // [bh][w]   bottom row of every block row
+    uint8_t* right;  // [bw][h]   right column of every block column
+    int* dc;         // [bh][bw]
+    uint8_t* mode;   // [bh][bw]
+};
+__host__ __device__ inline size_t intra_smem_bytes(const Geom& g)
+{
+    return (size_t)g.bh * g.w + (size_t)g.bw * g.h + (size_t)g.bh * g.bw * 5 + 16;
+}
+
+template <int DECODE>
+__global__ void __launch_bounds__(IW_THREADS) intra_luma_kernel(Geom g, FramePtrs p, Step st)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double s_tile[IW_THREADS / 8][72];
+    __shared__ __align__(16) int16_t s_lv[IW_THREADS / 8][64];
+    IntraSmem sm;
+    sm.dc = (int*)s_raw;
+    sm.bot = s_raw + (size_t)g.bh * g.bw * 4;
+    sm.right = sm.bot + (size_t)g.bh * g.w;
+    sm.mode = sm.right + (size_t)g.bw * g.h;
+    constexpr int TAB = DECODE ? 1 : 0;
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7, ngrp = IW_THREADS / 8;
+    const int gop = blockIdx.x;
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const uint8_t* cury = p.cur + f * g.fb;
+    uint8_t* recy = p.rec + f * g.fb;
+    const int bw = g.bw, bh = g.bh, w = g.w;
+    const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
+
+    for (int wv = 0; wv < nwaves; wv++) {
+        const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
+        for (int by0 = by_lo; by0 <= by_hi; by0 += ngrp) {  // whole warps iterate together
+            const int by = by0 + grp;
+            const bool active = by <= by_hi;
+            const int bx = active ? wv - 2 * by : 0, byy = active ? by : 0;
+            const bool hasL = bx > 0, hasU = byy > 0;
+            const int mb = (byy >> 1) * g.mbw + (bx >> 1), k = ((byy & 1) << 1) | (bx & 1);
+
+            // neighbours from the reconstructed plane (shared-memory edges)
+            int up[8], left_r, sumU = 0;
+#pragma unroll
+            for (int x = 0; x < 8; x++) { up[x] = hasU ? sm.bot[(byy - 1) * w + bx * 8 + x] : 128; sumU += up[x]; }
+            const int up_r = hasU ? sm.bot[(byy - 1) * w + bx * 8 + r] : 128;   // column r's own upper neighbour
+            left_r = hasL ? sm.right[(bx - 1) * g.h + byy * 8 + r] : 128;
+            const int sumL = group_sum(left_r);
+            // predVal = (predValLeft + predValUpper) / 16.0, a missing side contributes 128*8 (ENC:711-733)
+            const double pd = __ddiv_rn((double)((hasL ? sumL : 1024) + (hasU ? sumU : 1024)), 16.0);
+
+            int mode;
+            int e[8];
+            if (!DECODE) {
+                const uint2 cwd = *(const uint2*)(cury + (size_t)(byy * 8 + r) * w + bx * 8);
+                int c[8], e0[8], e1[8], e2[8], sae0 = 0, sae1 = 0, sae2 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { c[i] = (cwd.x >> (8 * i)) & 255; c[4 + i] = (cwd.y >> (8 * i)) & 255; }
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    e0[x] = c[x] - up[x];                                       // DPCM_pix_0 (vertical)
+                    e1[x] = c[x] - left_r;                                      // DPCM_pix_1 (horizontal)
+                    e2[x] = __double2int_rz(__dsub_rn((double)c[x], pd));       // DPCM_pix_2 (DC): (int)(cur - predVal)
+                    sae0 += abs(e0[x]); sae1 += abs(e1[x]); sae2 += abs(e2[x]);
+                }
+                sae0 = group_sum(sae0); sae1 = group_sum(sae1); sae2 = group_sum(sae2);
+                if (hasL && hasU) {
+                    const int m = min(min(sae0, sae1), sae2);
+                    mode = (m == sae0) ? 0 : ((m == sae1) ? 1 : 2);             // ENC:958-976
+                } else if (hasL) mode = (sae2 > sae1) ? 1 : 2;                  // ENC:897-908
+                else if (hasU) mode = (sae2 > sae0) ? 0 : 2;
+                else mode = 2;
+#pragma unroll
+                for (int x = 0; x < 8; x++) e[x] = mode == 0 ? e0[x] : (mode == 1 ? e1[x] : e2[x]);
+            }
+            // mode predictor p (ENC:1334-1350 / decoder inverse ENC:1793-1795)
+            int pm = 2;
+            if (hasL && hasU) pm = med3(sm.mode[byy * bw + bx - 1], sm.mode[(byy - 1) * bw + bx - 1], sm.mode[(byy - 1) * bw + bx]);
+            else if (hasL) pm = sm.mode[byy * bw + bx - 1];
+            else if (hasU) pm = sm.mode[(byy - 1) * bw + bx];
+            const size_t mi = (f * g.nmb + mb) * 4 + k;
+            if (!DECODE) {
+                int mpmf = 0, bit = 0;
+                if (hasL || hasU) {
+                    mpmf = (mode == pm);
+                    if (!mpmf) bit = (pm == 0) ? (mode == 1 ? 0 : 1) : (mode == 0 ? 0 : 1);
+                }
+                if (active && r == 0) { p.mpm[mi] = (uint8_t)mpmf; p.ipm[mi] = (uint8_t)bit; }
+            } else {
+                const int mpmf = p.mpm[mi], bit = p.ipm[mi];
+                if (!hasL && !hasU) mode = 2;
+                else if (mpmf) mode = pm;
+                else if (pm == 0) mode = bit == 0 ? 1 : 2;
+                else if (pm == 2) mode = bit == 0 ? 0 : 1;
+                else mode = bit == 0 ? 0 : 2;
+            }
+
+            int16_t* lv = p.levels + ((f * g.nmb + mb) * 6 + k) * 64;
+            int q[8];  // dequantised coefficients of ROW r after the transposition below
+            int P = 0;
+            if (r == 0) P = dc_pred_luma(sm.dc, bw, bx, byy);
+            if (!DECODE) {
+                double t[8], D[8];
+                fdct_row(e, t);
+                group_transpose(t, s_tile[grp], r);
+                fdct_col(t, r, D);
+                if (r == 0) D[0] = __dsub_rn(D[0], (double)P);
+                int nz = 0, L[8];
+#pragma unroll
+                for (int v = 0; v < 8; v++) {
+                    L[v] = quant(D[v], (v == 0 && r == 0) ? st.qdc : st.qac, false);
+                    s_lv[grp][c_IZ[v * 8 + r]] = (int16_t)L[v];
+                    if (!(v == 0 && r == 0)) nz |= L[v];
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, nz != 0);
+                __syncwarp();
+                if (active) {
+                    *(uint4*)(lv + 8 * r) = *(const uint4*)(&s_lv[grp][8 * r]);
+                    if (r == 0) p.acflag[(f * g.nmb + mb) * 6 + k] = ((bal >> (8 * (grp & 3))) & 0xffu) ? 0 : 1;
+                }
+            } else {
+                *(uint4*)(&s_lv[grp][8 * r]) = *(const uint4*)(lv + 8 * r);
+                __syncwarp();
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][c_IZ[r * 8 + u]] * ((r == 0 && u == 0) ? st.qdc : st.qac);
+            if (r == 0) { q[0] += P; if (active) sm.dc[byy * bw + bx] = q[0]; }
+            double t2[8], R[8];
+            idct_row<TAB>(q, t2);
+            group_transpose(t2, s_tile[grp], r);
+            idct_col<TAB>(t2, R);   // lane r holds column x=r
+
+            // IDPCM_pix_0/1/2 (ENC:744-850): (int)(idct + pred) with the sum formed in double, then clipped
+            int lefts[8];
+#pragma unroll
+            for (int y = 0; y < 8; y++) lefts[y] = __shfl_sync(0xffffffffu, left_r, (threadIdx.x & 24) | y);
+            uint8_t out[8];
+#pragma unroll
+            for (int y = 0; y < 8; y++) {
+                const double pv = mode == 0 ? (double)up_r : (mode == 1 ? (double)lefts[y] : pd);
+                out[y] = (uint8_t)clip255(__double2int_rz(__dadd_rn(R[y], pv)));
+            }
+            uint8_t* px = (uint8_t*)s_lv[grp];
+            __syncwarp();
+#pragma unroll
+            for (int y = 0; y < 8; y++) px[y * 8 + r] = out[y];
+            __syncwarp();
+            if (active) {
+                *(uint2*)(recy + (size_t)(byy * 8 + r) * w + bx * 8) = *(const uint2*)(&px[8 * r]);
+                sm.bot[byy * w + bx * 8 + r] = out[7];
+                if (r == 7) {
+#pragma unroll
+                    for (int y = 0; y < 8; y++) sm.right[bx * g.h + byy * 8 + y] = out[y];
+                }
+                if (r == 0) sm.mode[byy * bw + bx] = (uint8_t)mode;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================
+// Motion estimation (R1, R2).  One CTA per macroblock row per frame: the current rows and the 48-row search
+// window of the previous reconstruction (apron built with clamp + the reference's zero last row/column) are
+// staged in shared memory with 16-byte loads; one warp per macroblock, two candidates per lane, packed-byte
+// SAD, ballot/shuffle winner selection reproducing visiting order, strict-< tie-break and the second-zero
+// early break.  `fixup` == 1 re-evaluates only macroblocks whose carried start state turned out != 0.
+// =====================================================================================================
+__device__ __forceinline__ uint4 window_chunk(const uint8_t* __restrict__ plane, int w, int h, int py, int pxc)
+{   // 16 bytes of the padded image (pad 16) at padded row py, padded columns [16*pxc, 16*pxc+16)
+    const int PH = h + 32, PW = w + 32;
+    if (py == PH - 1) return make_uint4(0, 0, 0, 0);
+    const int yy = min(max(py - 16, 0), h - 1);
+    const uint8_t* row = plane + (size_t)yy * w;
+    const int x0 = pxc * 16 - 16;
+    if (x0 >= 0 && x0 + 16 <= w) return __ldg((const uint4*)(row + x0));
+    uint32_t v;
+    if (x0 < 0) { v = row[0]; v *= 0x01010101u; return make_uint4(v, v, v, v); }
+    v = row[w - 1]; v *= 0x01010101u;
+    uint4 o = make_uint4(v, v, v, v);
+    if (pxc * 16 + 16 == PW) o.w &= 0x00ffffffu;  // last padded column stays 0
+    return o;
+}
+
+__global__ void __launch_bounds__(1024) me_sad_kernel(Geom g, FramePtrs p, Step st, int fixup)
+{
+    extern __shared__ __align__(16) unsigned char s_me[];
+    const int gop = blockIdx.y, mby = blockIdx.x;
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const uint8_t* states = p.mestate + (size_t)gop * g.nmb + mby * g.mbw;
+    if (fixup) {
+        if (p.meflag[gop] == 0) return;
+        int any = 0;
+        for (int i = threadIdx.x; i < g.mbw; i += blockDim.x) any |= states[i];
+        if (!__syncthreads_or(any)) return;
+    }
+    const int pitch = g.w + 32;                 // bytes per window row
+    uint8_t* s_win = s_me;                      // [48][pitch]
+    uint8_t* s_cur = s_me + 48 * pitch;         // [16][w]
+    const uint8_t* cury = p.cur + f * g.fb;
+    const uint8_t* refy = p.rec + (f - 1) * g.fb;
+    const int chunks = pitch / 16;
+    for (int i = threadIdx.x; i < 48 * chunks; i += blockDim.x) {
+        const int row = i / chunks, c = i - row * chunks;
+        *(uint4*)(s_win + row * pitch + c * 16) = window_chunk(refy, g.w, g.h, mby * 16 + row, c);
+    }
+    for (int i = threadIdx.x; i < 16 * (g.w / 16); i += blockDim.x) {
+        const int row = i / (g.w / 16), c = i - row * (g.w / 16);
+        *(uint4*)(s_cur + row * g.w + c * 16) = __ldg((const uint4*)(cury + (size_t)(mby * 16 + row) * g.w + c * 16));
+    }
+    __syncthreads();
+
+    for (int mbx = warp; mbx < g.mbw; mbx += nwarps) {
+        const int state = fixup ? states[mbx] : 0;
+        if (fixup && state == 0) continue;
+        uint32_t sad[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int idx = lane + 32 * h2;
+            const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
+            const int col = mbx * 16 + 16 + dx;          // padded column of the candidate's first pixel
+            const uint32_t* wrow = (const uint32_t*)(s_win + (16 + dy) * pitch + (col & ~3));
+            const int sh = (col & 3) * 8;
+            const uint32_t* crow = (const uint32_t*)(s_cur + mbx * 16);
+            uint32_t acc = 0;
+#pragma unroll 4
+            for (int j = 0; j < 16; j++) {
+                const uint32_t w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3], w4 = wrow[4];
+                acc = __vsadu4(__funnelshift_r(w0, w1, sh), crow[0]) + acc;
+                acc = __vsadu4(__funnelshift_r(w1, w2, sh), crow[1]) + acc;
+                acc = __vsadu4(__funnelshift_r(w2, w3, sh), crow[2]) + acc;
+                acc = __vsadu4(__funnelshift_r(w3, w4, sh), crow[3]) + acc;
+                wrow += pitch / 4;
+                crow += g.w / 4;
+            }
+            sad[h2] = acc;
+        }
+        // zero-SAD visits in visiting order; the search breaks at the SECOND one (ENC:2130-2141)
+        const unsigned long long z = (unsigned long long)__ballot_sync(0xffffffffu, sad[0] == 0) |
+                                     ((unsigned long long)__ballot_sync(0xffffffffu, sad[1] == 0) << 32);
+        int win, moves = 64;
+        uint32_t best;
+        if (__popcll(z) >= 2) {
+            win = __ffsll((long long)(z & (z - 1))) - 1;
+            moves = win + 1;
+            best = 0;
+        } else {   // first visited minimum: min over key = SAD*64 + visit index
+            uint32_t key = min(sad[0] * 64u + lane, sad[1] * 64u + lane + 32u);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+            win = key & 63; best = key >> 6;
+        }
+        if (lane == 0) {
+            const int mb = mby * g.mbw + mbx;
+            // mv = MB origin - best position (ENC:2145-2146)
+            p.mv[(f * g.nmb + mb) * 2] = (int16_t)(-c_cand[state][win][0]);
+            p.mv[(f * g.nmb + mb) * 2 + 1] = (int16_t)(-c_cand[state][win][1]);
+            p.minsad[f * g.nmb + mb] = (int32_t)best;
+            if (!fixup) {
+                p.memoves[(size_t)gop * g.nmb + mb] = (uint8_t)moves;
+                if (moves < 64) atomicAdd(&p.meflag[gop], 1u);
+            }
+        }
+    }
+}
+
+// Exact fallback, pass 1: for frames where some search broke early, find for every macroblock and every one of
+// the 8 possible start states which visits have SAD == 0 (block identical to the candidate).  The break point
+// of a search depends only on these masks, never on non-zero SAD values.
+__global__ void __launch_bounds__(1024) me_zero_kernel(Geom g, FramePtrs p, Step st)
+{
+    extern __shared__ __align__(16) unsigned char s_me[];
+    const int gop = blockIdx.y, mby = blockIdx.x;
+    if (p.meflag[gop] == 0) return;
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int pitch = g.w + 32;
+    uint8_t* s_win = s_me;
+    uint8_t* s_cur = s_me + 48 * pitch;
+    const uint8_t* cury = p.cur + f * g.fb;
+    const uint8_t* refy = p.rec + (f - 1) * g.fb;
+    const int chunks = pitch / 16;
+    for (int i = threadIdx.x; i < 48 * chunks; i += blockDim.x) {
+        const int row = i / chunks, c = i - row * chunks;
+        *(uint4*)(s_win + row * pitch + c * 16) = window_chunk(refy, g.w, g.h, mby * 16 + row, c);
+    }
+    for (int i = threadIdx.x; i < 16 * (g.w / 16); i += blockDim.x) {
+        const int row = i / (g.w / 16), c = i - row * (g.w / 16);
+        *(uint4*)(s_cur + row * g.w + c * 16) = __ldg((const uint4*)(cury + (size_t)(mby * 16 + row) * g.w + c * 16));
+    }
+    __syncthreads();
+    for (int mbx = warp; mbx < g.mbw; mbx += nwarps) {
+        for (int state = 0; state < 8; state++) {
+            unsigned long long z = 0;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+                const int idx = lane + 32 * h2;
+                const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
+                const int col = mbx * 16 + 16 + dx;
+                const uint32_t* wrow = (const uint32_t*)(s_win + (16 + dy) * pitch + (col & ~3));
+                const int sh = (col & 3) * 8;
+                const uint32_t* crow = (const uint32_t*)(s_cur + mbx * 16);
+                uint32_t diff = 0;
+                for (int j = 0; j < 16 && diff == 0; j++) {   // early out on the first differing row
+                    const uint32_t w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3], w4 = wrow[4];
+                    diff |= __funnelshift_r(w0, w1, sh) ^ crow[0];
+                    diff |= __funnelshift_r(w1, w2, sh) ^ crow[1];
+                    diff |= __funnelshift_r(w2, w3, sh) ^ crow[2];
+                    diff |= __funnelshift_r(w3, w4, sh) ^ crow[3];
+                    wrow += pitch / 4;
+                    crow += g.w / 4;
+                }
+                z |= (unsigned long long)__ballot_sync(0xffffffffu, diff == 0) << (32 * h2);
+            }
+            if (lane == 0) p.mezero[((size_t)gop * g.nmb + mby * g.mbw + mbx) * 8 + state] = z;
+        }
+    }
+}
+
+// Exact fallback, pass 2: resolve the carried spiral state of every macroblock of a flagged frame.  A search
+// started in state s makes m = (index of its second zero-SAD visit)+1 moves, or 64; the state handed to the next
+// macroblock is c_next[s][m] (ENC:2094-2095: flag/xflag/yflag are initialised once per frame, never per MB).
+__global__ void __launch_bounds__(32) me_chain_kernel(Geom g, FramePtrs p)
+{
+    const int gop = blockIdx.x;
+    if (p.meflag[gop] == 0) return;
+    if (threadIdx.x != 0) return;
+    const unsigned long long* zm = p.mezero + (size_t)gop * g.nmb * 8;
+    uint8_t* states = p.mestate + (size_t)gop * g.nmb;
+    int s = 0;
+    for (int mb = 0; mb < g.nmb; mb++) {
+        states[mb] = (uint8_t)s;
+        const unsigned long long z = zm[mb * 8 + s];
+        int m = 64;
+        if (__popcll(z) >= 2) m = __ffsll((long long)(z & (z - 1)));
+        s = c_next[s][m];
+    }
+}
+
+// ---- unit shims ------------------------------------------------------------------------------------
+__global__ void dct8x8_kernel(const int32_t* in, double* out, int n)
+{
+    __shared__ double s_tile[16][72];
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int blk = blockIdx.x * 16 + grp;
+    const int bsafe = min(blk, n - 1);
+    int e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = in[(size_t)bsafe * 64 + r * 8 + i];
+    double t[8], D[8];
+    fdct_row(e, t);
+    group_transpose(t, s_tile[grp], r);
+    fdct_col(t, r, D);
+    if (blk < n)
+#pragma unroll
+        for (int v = 0; v < 8; v++) out[(size_t)blk * 64 + v * 8 + r] = D[v];
+}
+template <int TAB>
+__global__ void idct8x8_kernel(const int32_t* in, double* out, int n)
+{
+    __shared__ double s_tile[16][72];
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int blk = blockIdx.x * 16 + grp;
+    const int bsafe = min(blk, n - 1);
+    int q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = in[(size_t)bsafe * 64 + r * 8 + i];
+    double t[8], R[8];
+    idct_row<TAB>(q, t);
+    group_transpose(t, s_tile[grp], r);
+    idct_col<TAB>(t, R);
+    if (blk < n)
+#pragma unroll
+        for (int y = 0; y < 8; y++) out[(size_t)blk * 64 + y * 8 + r] = R[y];
+}
+
+// decoder: motion vector reconstruction mv = mvd + Pm over already reconstructed neighbours (DEC:4301-4370).
+// One warp per frame, waves w = mbx + 2*mby (L, U, UL, UR dependencies).
+__global__ void __launch_bounds__(32) mv_recon_kernel(Geom g, FramePtrs p, Step st)
+{
+    const int gop = blockIdx.x, lane = threadIdx.x;
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const int16_t* mvd = p.mvd + f * g.nmb * 2;
+    int16_t* mv = p.mv + f * g.nmb * 2;
+    const int nwaves = (g.mbw - 1) + 2 * (g.mbh - 1) + 1;
+    for (int wv = 0; wv < nwaves; wv++) {
+        const int lo = max(0, (wv - (g.mbw - 1) + 1) >> 1), hi = min(g.mbh - 1, wv >> 1);
+        for (int mby = lo + lane; mby <= hi; mby += 32) {
+            const int mb = mby * g.mbw + (wv - 2 * mby);
+            int px, py;
+            mv_predictor(mv, g.mbw, mb, px, py);
+            mv[2 * mb] = (int16_t)(mvd[2 * mb] + px);
+            mv[2 * mb + 1] = (int16_t)(mvd[2 * mb + 1] + py);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace icsp

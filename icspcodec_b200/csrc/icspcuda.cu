@@ -1,0 +1,563 @@
+// libicspcuda: C ABI (include/icspcuda.h) over the sm_100a kernels in icsp_kernels.cuh.
+// Host side only orchestrates: one context = one GPU, one stream, SoA device buffers sized for max_frames.
+#include "../../include/icspcuda.h"
+#include "icsp_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace icsp;
+
+namespace {
+
+thread_local char g_create_error[256] = "";
+
+enum KernelId {
+    K_INTRA_ENC = 0, K_INTRA_DEC, K_FDCT, K_DCCHAIN, K_IDCT_ENC, K_IDCT_DEC, K_ME_SAD, K_ME_ZERO, K_ME_CHAIN, K_ME_FIXUP,
+    K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_COUNT
+};
+const char* const kKernelNames[K_COUNT] = {
+    "intra_luma_kernel<enc>", "intra_luma_kernel<dec>", "fdct_quant_kernel", "dc_chain_kernel", "idct_recon_kernel<enc>",
+    "idct_recon_kernel<dec>", "me_sad_kernel", "me_zero_kernel", "me_chain_kernel", "me_sad_kernel(fixup)",
+    "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel"};
+
+struct Pending { int k; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct icsp_ctx {
+    int device = 0;
+    Geom g{};
+    int cap = 0;  // frames
+    cudaStream_t stream = nullptr;
+    // device SoA
+    uint8_t *d_cur = nullptr, *d_rec = nullptr, *d_acflag = nullptr, *d_mpm = nullptr, *d_ipm = nullptr;
+    int16_t *d_levels = nullptr, *d_mvd = nullptr, *d_mv = nullptr;
+    int32_t* d_minsad = nullptr;
+    double* d_dcraw = nullptr;
+    int32_t* d_dcrec = nullptr;
+    uint8_t *d_mestate = nullptr, *d_memoves = nullptr;
+    uint32_t* d_meflag = nullptr;
+    unsigned long long* d_mezero = nullptr;
+    void* d_shim = nullptr;
+    size_t shim_bytes = 0;
+    // instrumentation
+    bool profiling = false;
+    uint64_t launches = 0;
+    double total_ms[K_COUNT] = {};
+    uint64_t count[K_COUNT] = {};
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> free_events;
+    cudaEvent_t slots[8] = {};
+    char err[256] = "";
+    size_t me_smem = 0, intra_smem = 0, chain_smem = 0;
+};
+
+namespace {
+
+int fail(icsp_ctx* c, int code, const char* fmt, ...)
+{
+    char* dst = c ? c->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(c, ICSP_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int geom_init(Geom& g, int w, int h)
+{
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15)) return -1;
+    g.w = w; g.h = h; g.mbw = w / 16; g.mbh = h / 16; g.nmb = g.mbw * g.mbh;
+    g.cw = w / 2; g.ch = h / 2; g.bw = w / 8; g.bh = h / 8; g.fb = w * h * 3 / 2;
+    return 0;
+}
+
+// ---- constant tables ---------------------------------------------------------------------------------
+int upload_tables(icsp_ctx* c)
+{
+    static const double LIT[8] = {1.0, 0.980785, 0.92388, 0.83147, 0.707107, 0.55557, 0.382683, 0.19509};
+    double T[2][8][8];
+    // costable[u][x] ~ cos((2x+1)u*pi/16) as 6-digit literals (ENC.h:191-198 / DEC.h:20-27): pick literal by angle
+    for (int u = 0; u < 8; u++)
+        for (int x = 0; x < 8; x++) {
+            int k = ((2 * x + 1) * u) % 32;       // angle k*pi/16, period 32
+            int sgn = 1;
+            if (k > 16) k = 32 - k;               // cos(2pi - a) = cos a
+            if (k > 8) { k = 16 - k; sgn = -1; }  // cos(pi - a) = -cos a
+            // k in [0,8]; k == 8 never occurs for odd (2x+1)*u multiples except u==0 handled by k==0
+            double lit = (k == 8) ? 0.0 : LIT[k];
+            T[1][u][x] = sgn * lit;
+            T[0][u][x] = (double)(float)(sgn * lit);
+        }
+    const double irt2 = 1.0 / std::sqrt(2.0);
+    static const unsigned char ZZ[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                         41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                         30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    unsigned char IZ[64];
+    for (int k = 0; k < 64; k++) IZ[ZZ[k]] = (unsigned char)k;
+    // spiral visiting order for each of the 8 carried start states (motionEstimation ENC:2094-2143)
+    signed char cand[8][64][2];
+    unsigned char next[8][65];
+    for (int s = 0; s < 8; s++) {
+        int flag = s & 1, xflag = (s & 2) ? -1 : 1, yflag = (s & 4) ? 1 : -1;
+        int x = 0, y = 0, xcnt = 0, ycnt = 0;
+        next[s][0] = (unsigned char)s;
+        for (int it = 0; it < 64; it++) {
+            if (!flag) { if (xflag <= 0) x += xcnt; else x -= xcnt; flag = 1; xcnt++; xflag = -xflag; }
+            else { if (yflag < 0) y += ycnt; else y -= ycnt; flag = 0; ycnt++; yflag = -yflag; }
+            cand[s][it][0] = (signed char)x;
+            cand[s][it][1] = (signed char)y;
+            next[s][it + 1] = (unsigned char)(flag | (xflag < 0 ? 2 : 0) | (yflag > 0 ? 4 : 0));
+        }
+    }
+    CU(cudaMemcpyToSymbol(c_T, T, sizeof(T)));
+    CU(cudaMemcpyToSymbol(c_irt2, &irt2, sizeof(irt2)));
+    CU(cudaMemcpyToSymbol(c_ZZ, ZZ, sizeof(ZZ)));
+    CU(cudaMemcpyToSymbol(c_IZ, IZ, sizeof(IZ)));
+    CU(cudaMemcpyToSymbol(c_cand, cand, sizeof(cand)));
+    CU(cudaMemcpyToSymbol(c_next, next, sizeof(next)));
+    return ICSP_OK;
+}
+
+// ---- launch bookkeeping ------------------------------------------------------------------------------
+cudaEvent_t get_event(icsp_ctx* c)
+{
+    if (!c->free_events.empty()) { cudaEvent_t e = c->free_events.back(); c->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void fold_pending(icsp_ctx* c)
+{
+    if (c->pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : c->pending) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        c->total_ms[p.k] += ms;
+        c->free_events.push_back(p.a);
+        c->free_events.push_back(p.b);
+    }
+    c->pending.clear();
+}
+struct LaunchScope {
+    icsp_ctx* c; int k; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(icsp_ctx* c_, int k_) : c(c_), k(k_)
+    {
+        c->launches++; c->count[k]++;
+        if (c->profiling) {
+            if (c->pending.size() > 8192) fold_pending(c);
+            a = get_event(c); b = get_event(c);
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~LaunchScope()
+    {
+        if (c->profiling) { cudaEventRecord(b, c->stream); c->pending.push_back({k, a, b}); }
+    }
+};
+
+FramePtrs frame_ptrs(icsp_ctx* c)
+{
+    FramePtrs p;
+    p.cur = c->d_cur; p.rec = c->d_rec; p.levels = c->d_levels; p.acflag = c->d_acflag; p.mpm = c->d_mpm; p.ipm = c->d_ipm;
+    p.mvd = c->d_mvd; p.mv = c->d_mv; p.minsad = c->d_minsad; p.dcraw = c->d_dcraw; p.dcrec = c->d_dcrec;
+    p.mestate = c->d_mestate; p.memoves = c->d_memoves; p.meflag = c->d_meflag; p.mezero = c->d_mezero;
+    return p;
+}
+
+int check_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
+{
+    if (!c) return ICSP_ERR_PARAM;
+    if (n_gops <= 0 || gop_len <= 0 || qdc <= 0 || qac <= 0) return fail(c, ICSP_ERR_PARAM, "bad n_gops/gop_len/qp");
+    if (n_gops > 65535) return fail(c, ICSP_ERR_PARAM, "n_gops > 65535 per call");
+    if ((long long)n_gops * gop_len > c->cap) return fail(c, ICSP_ERR_CAPACITY, "%d frames > capacity %d", n_gops * gop_len, c->cap);
+    return ICSP_OK;
+}
+
+int me_threads(const Geom& g) { return g.mbw * 32 > 1024 ? 1024 : g.mbw * 32; }
+
+// motion estimation of step t for every GOP: speculative state-0 search, then the exact carried-state fallback
+// (no-ops unless some search of the frame broke early)
+int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G)
+{
+    const Geom& g = c->g;
+    CU(cudaMemsetAsync(c->d_meflag, 0, sizeof(uint32_t) * G, c->stream));
+    CU(cudaMemsetAsync(c->d_mestate, 0, (size_t)G * g.nmb, c->stream));
+    dim3 grid(g.mbh, G);
+    { LaunchScope ls(c, K_ME_SAD); me_sad_kernel<<<grid, me_threads(g), c->me_smem, c->stream>>>(g, p, st, 0); }
+    { LaunchScope ls(c, K_ME_ZERO); me_zero_kernel<<<grid, me_threads(g), c->me_smem, c->stream>>>(g, p, st); }
+    { LaunchScope ls(c, K_ME_CHAIN); me_chain_kernel<<<G, 32, 0, c->stream>>>(g, p); }
+    { LaunchScope ls(c, K_ME_FIXUP); me_sad_kernel<<<grid, me_threads(g), c->me_smem, c->stream>>>(g, p, st, 1); }
+    return ICSP_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+const char* icsp_version(void) { return "libicspcuda 0.1 (sm_100a)"; }
+
+const char* icsp_last_error(const icsp_ctx* c) { return c ? c->err : g_create_error; }
+
+int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frames)
+{
+    icsp_ctx* c = nullptr;
+    if (!out) return fail(nullptr, ICSP_ERR_PARAM, "ctx out pointer is NULL");
+    *out = nullptr;
+    Geom g;
+    if (geom_init(g, width, height)) return fail(nullptr, ICSP_ERR_PARAM, "width/height must be positive multiples of 16");
+    if (max_frames <= 0) return fail(nullptr, ICSP_ERR_PARAM, "max_frames must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ICSP_ERR_CUDA, "no CUDA device: %s (libicspcuda has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, ICSP_ERR_PARAM, "device %d out of range (%d devices)", device, ndev);
+    c = new (std::nothrow) icsp_ctx();
+    if (!c) return fail(nullptr, ICSP_ERR_NOMEM, "host allocation failed");
+    c->device = device; c->g = g; c->cap = max_frames;
+    auto bail = [&](int code) { snprintf(g_create_error, sizeof(g_create_error), "%s", c->err); icsp_destroy(c); return code; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, ICSP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? ICSP_ERR_NOMEM : ICSP_ERR_CUDA); } } while (0)
+    CUB(cudaSetDevice(device));
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t F = (size_t)max_frames, nmb = (size_t)g.nmb;
+    CUB(cudaMalloc(&c->d_cur, F * g.fb + 64));
+    CUB(cudaMalloc(&c->d_rec, F * g.fb + 64));
+    CUB(cudaMalloc(&c->d_levels, F * nmb * 384 * sizeof(int16_t)));
+    CUB(cudaMalloc(&c->d_acflag, F * nmb * 6));
+    CUB(cudaMalloc(&c->d_mpm, F * nmb * 4));
+    CUB(cudaMalloc(&c->d_ipm, F * nmb * 4));
+    CUB(cudaMalloc(&c->d_mvd, F * nmb * 2 * sizeof(int16_t)));
+    CUB(cudaMalloc(&c->d_mv, F * nmb * 2 * sizeof(int16_t)));
+    CUB(cudaMalloc(&c->d_minsad, F * nmb * sizeof(int32_t)));
+    // per-GOP scratch: at most max_frames GOPs (gop_len == 1)
+    CUB(cudaMalloc(&c->d_dcraw, F * nmb * 6 * sizeof(double)));
+    CUB(cudaMalloc(&c->d_dcrec, F * nmb * 6 * sizeof(int32_t)));
+    CUB(cudaMalloc(&c->d_mestate, F * nmb));
+    CUB(cudaMalloc(&c->d_memoves, F * nmb));
+    CUB(cudaMalloc(&c->d_meflag, F * sizeof(uint32_t)));
+    CUB(cudaMalloc(&c->d_mezero, F * nmb * 8 * sizeof(unsigned long long)));
+    CUB(cudaMemsetAsync(c->d_mpm, 0, F * nmb * 4, c->stream));
+    CUB(cudaMemsetAsync(c->d_ipm, 0, F * nmb * 4, c->stream));
+    CUB(cudaMemsetAsync(c->d_mvd, 0, F * nmb * 4, c->stream));
+    CUB(cudaMemsetAsync(c->d_mv, 0, F * nmb * 4, c->stream));
+    CUB(cudaMemsetAsync(c->d_minsad, 0, F * nmb * 4, c->stream));
+    for (auto& s : c->slots) CUB(cudaEventCreate(&s));
+    if (upload_tables(c) != ICSP_OK) return bail(ICSP_ERR_CUDA);
+    c->me_smem = (size_t)48 * (g.w + 32) + (size_t)16 * g.w + 32;
+    c->intra_smem = intra_smem_bytes(g);
+    c->chain_smem = (size_t)6 * g.nmb * sizeof(int);
+    if (c->me_smem > 200 * 1024 || c->intra_smem > 180 * 1024 || c->chain_smem > 200 * 1024) {
+        fail(c, ICSP_ERR_PARAM, "frame %dx%d too large for the shared-memory staging of this build", width, height);
+        return bail(ICSP_ERR_PARAM);
+    }
+    CUB(cudaFuncSetAttribute(me_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->me_smem));
+    CUB(cudaFuncSetAttribute(me_zero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->me_smem));
+    CUB(cudaFuncSetAttribute(intra_luma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->intra_smem));
+    CUB(cudaFuncSetAttribute(intra_luma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->intra_smem));
+    CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->chain_smem));
+    CUB(cudaStreamSynchronize(c->stream));
+#undef CUB
+    *out = c;
+    return ICSP_OK;
+}
+
+void icsp_destroy(icsp_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto& e : c->free_events) cudaEventDestroy(e);
+    for (auto& s : c->slots) if (s) cudaEventDestroy(s);
+    void* bufs[] = {c->d_cur, c->d_rec, c->d_levels, c->d_acflag, c->d_mpm, c->d_ipm, c->d_mvd, c->d_mv, c->d_minsad, c->d_dcraw,
+                    c->d_dcrec, c->d_mestate, c->d_memoves, c->d_meflag, c->d_mezero, c->d_shim};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* icsp_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void icsp_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int icsp_sync(icsp_ctx* c)
+{
+    if (!c) return ICSP_ERR_PARAM;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return ICSP_OK;
+}
+
+// ---- encoder -------------------------------------------------------------------------------------------
+int icsp_enc_upload(icsp_ctx* c, const uint8_t* frames, int n_frames)
+{
+    if (!c || !frames || n_frames <= 0) return fail(c, ICSP_ERR_PARAM, "icsp_enc_upload: bad arguments");
+    if (n_frames > c->cap) return fail(c, ICSP_ERR_CAPACITY, "%d frames > capacity %d", n_frames, c->cap);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->d_cur, frames, (size_t)n_frames * c->g.fb, cudaMemcpyHostToDevice, c->stream));
+    return ICSP_OK;
+}
+
+int icsp_enc_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
+{
+    int rc = check_run(c, n_gops, gop_len, qdc, qac);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    const Geom& g = c->g;
+    const FramePtrs p = frame_ptrs(c);
+    const int G = n_gops;
+    for (int t = 0; t < gop_len; t++) {
+        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0};
+        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
+        if (st.intra) {
+            LaunchScope ls(c, K_INTRA_ENC);
+            intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, c->stream>>>(g, p, st);
+        } else {
+            rc = launch_me(c, p, st, G);
+            if (rc) return rc;
+        }
+        { LaunchScope ls(c, K_FDCT); fdct_quant_kernel<<<tgrid, TR_THREADS, 0, c->stream>>>(g, p, st); }
+        { LaunchScope ls(c, K_DCCHAIN); dc_chain_kernel<<<G, 128, c->chain_smem, c->stream>>>(g, p, st, 0); }
+        { LaunchScope ls(c, K_IDCT_ENC); idct_recon_kernel<0><<<tgrid, TR_THREADS, 0, c->stream>>>(g, p, st); }
+    }
+    CU(cudaGetLastError());
+    return ICSP_OK;
+}
+
+int icsp_enc_download(icsp_ctx* c, int n, const icsp_enc_out* o)
+{
+    if (!c || !o || n <= 0) return fail(c, ICSP_ERR_PARAM, "icsp_enc_download: bad arguments");
+    if (n > c->cap) return fail(c, ICSP_ERR_CAPACITY, "%d frames > capacity %d", n, c->cap);
+    CU(cudaSetDevice(c->device));
+    const size_t N = (size_t)n, nmb = (size_t)c->g.nmb;
+    if (o->levels) CU(cudaMemcpyAsync(o->levels, c->d_levels, N * nmb * 384 * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (o->acflag) CU(cudaMemcpyAsync(o->acflag, c->d_acflag, N * nmb * 6, cudaMemcpyDeviceToHost, c->stream));
+    if (o->mpm) CU(cudaMemcpyAsync(o->mpm, c->d_mpm, N * nmb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o->ipm) CU(cudaMemcpyAsync(o->ipm, c->d_ipm, N * nmb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o->mvd) CU(cudaMemcpyAsync(o->mvd, c->d_mvd, N * nmb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o->mv) CU(cudaMemcpyAsync(o->mv, c->d_mv, N * nmb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o->minsad) CU(cudaMemcpyAsync(o->minsad, c->d_minsad, N * nmb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o->recon) CU(cudaMemcpyAsync(o->recon, c->d_rec, N * c->g.fb, cudaMemcpyDeviceToHost, c->stream));
+    return ICSP_OK;
+}
+
+int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len, int qdc, int qac, const icsp_enc_out* out)
+{
+    int rc = check_run(c, n_gops, gop_len, qdc, qac);
+    if (rc) return rc;
+    if (!frames || !out) return fail(c, ICSP_ERR_PARAM, "icsp_encode_gops: NULL frames/out");
+    const int n = n_gops * gop_len;
+    if ((rc = icsp_enc_upload(c, frames, n))) return rc;
+    // inter frames leave mpm/ipm untouched and intra frames leave mvd/mv/minsad untouched: clear them so the SoA
+    // rows of the other frame type read as zero, as documented
+    const size_t N = (size_t)n, nmb = (size_t)c->g.nmb;
+    CU(cudaMemsetAsync(c->d_mpm, 0, N * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_ipm, 0, N * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_mvd, 0, N * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_mv, 0, N * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_minsad, 0, N * nmb * 4, c->stream));
+    if ((rc = icsp_enc_run(c, n_gops, gop_len, qdc, qac))) return rc;
+    if ((rc = icsp_enc_download(c, n, out))) return rc;
+    return icsp_sync(c);
+}
+
+// ---- decoder -------------------------------------------------------------------------------------------
+int icsp_dec_upload(icsp_ctx* c, const icsp_dec_in* in, int n)
+{
+    if (!c || !in || !in->levels || !in->mpm || !in->ipm || !in->mvd || n <= 0)
+        return fail(c, ICSP_ERR_PARAM, "icsp_dec_upload: bad arguments");
+    if (n > c->cap) return fail(c, ICSP_ERR_CAPACITY, "%d frames > capacity %d", n, c->cap);
+    CU(cudaSetDevice(c->device));
+    const size_t N = (size_t)n, nmb = (size_t)c->g.nmb;
+    CU(cudaMemcpyAsync(c->d_levels, in->levels, N * nmb * 384 * 2, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_mpm, in->mpm, N * nmb * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_ipm, in->ipm, N * nmb * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_mvd, in->mvd, N * nmb * 4, cudaMemcpyHostToDevice, c->stream));
+    return ICSP_OK;
+}
+
+int icsp_dec_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
+{
+    int rc = check_run(c, n_gops, gop_len, qdc, qac);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    const Geom& g = c->g;
+    const FramePtrs p = frame_ptrs(c);
+    const int G = n_gops;
+    for (int t = 0; t < gop_len; t++) {
+        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0};
+        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
+        if (st.intra) {
+            LaunchScope ls(c, K_INTRA_DEC);
+            intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, c->stream>>>(g, p, st);
+        } else {
+            LaunchScope ls(c, K_MV_RECON);
+            mv_recon_kernel<<<G, 32, 0, c->stream>>>(g, p, st);
+        }
+        { LaunchScope ls(c, K_DCCHAIN); dc_chain_kernel<<<G, 128, c->chain_smem, c->stream>>>(g, p, st, 1); }
+        { LaunchScope ls(c, K_IDCT_DEC); idct_recon_kernel<1><<<tgrid, TR_THREADS, 0, c->stream>>>(g, p, st); }
+    }
+    CU(cudaGetLastError());
+    return ICSP_OK;
+}
+
+int icsp_dec_download(icsp_ctx* c, int n, uint8_t* out)
+{
+    if (!c || !out || n <= 0) return fail(c, ICSP_ERR_PARAM, "icsp_dec_download: bad arguments");
+    if (n > c->cap) return fail(c, ICSP_ERR_CAPACITY, "%d frames > capacity %d", n, c->cap);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out, c->d_rec, (size_t)n * c->g.fb, cudaMemcpyDeviceToHost, c->stream));
+    return ICSP_OK;
+}
+
+int icsp_decode_gops(icsp_ctx* c, const icsp_dec_in* in, int n_gops, int gop_len, int qdc, int qac, uint8_t* out)
+{
+    int rc = check_run(c, n_gops, gop_len, qdc, qac);
+    if (rc) return rc;
+    const int n = n_gops * gop_len;
+    if ((rc = icsp_dec_upload(c, in, n))) return rc;
+    if ((rc = icsp_dec_run(c, n_gops, gop_len, qdc, qac))) return rc;
+    if ((rc = icsp_dec_download(c, n, out))) return rc;
+    return icsp_sync(c);
+}
+
+// ---- shims -----------------------------------------------------------------------------------------------
+static int shim_reserve(icsp_ctx* c, size_t bytes)
+{
+    if (c->shim_bytes >= bytes) return ICSP_OK;
+    if (c->d_shim) cudaFree(c->d_shim);
+    c->d_shim = nullptr; c->shim_bytes = 0;
+    if (cudaMalloc(&c->d_shim, bytes) != cudaSuccess) return fail(c, ICSP_ERR_NOMEM, "shim buffer allocation failed");
+    c->shim_bytes = bytes;
+    return ICSP_OK;
+}
+
+int icsp_me_sad(icsp_ctx* c, const uint8_t* cur_y, const uint8_t* ref_y, int n, int16_t* mv, int32_t* minsad)
+{
+    if (!c || !cur_y || !ref_y || n <= 0 || !mv) return fail(c, ICSP_ERR_PARAM, "icsp_me_sad: bad arguments");
+    if (2 * n > c->cap) return fail(c, ICSP_ERR_CAPACITY, "icsp_me_sad needs capacity >= 2*n frames");
+    CU(cudaSetDevice(c->device));
+    const Geom& g = c->g;
+    const size_t ysz = (size_t)g.w * g.h;
+    // pair i: reference luma -> rec frame 2i, current luma -> cur frame 2i+1 (gop_len 2, step 1)
+    CU(cudaMemcpy2DAsync(c->d_rec, (size_t)2 * g.fb, ref_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpy2DAsync(c->d_cur + g.fb, (size_t)2 * g.fb, cur_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
+    Step st{2, 1, 1, 1, 0};
+    int rc = launch_me(c, frame_ptrs(c), st, n);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(mv, (size_t)g.nmb * 4, c->d_mv + (size_t)g.nmb * 2, (size_t)g.nmb * 8, (size_t)g.nmb * 4, n,
+                         cudaMemcpyDeviceToHost, c->stream));
+    if (minsad)
+        CU(cudaMemcpy2DAsync(minsad, (size_t)g.nmb * 4, c->d_minsad + g.nmb, (size_t)g.nmb * 8, (size_t)g.nmb * 4, n,
+                             cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    return icsp_sync(c);
+}
+
+int icsp_dct8x8(icsp_ctx* c, const int32_t* blocks, int n, double* out)
+{
+    if (!c || !blocks || !out || n <= 0) return fail(c, ICSP_ERR_PARAM, "icsp_dct8x8: bad arguments");
+    CU(cudaSetDevice(c->device));
+    int rc = shim_reserve(c, (size_t)n * 64 * 12);
+    if (rc) return rc;
+    int32_t* din = (int32_t*)c->d_shim;
+    double* dout = (double*)((char*)c->d_shim + (size_t)n * 64 * 4);
+    // keep the double region 8-byte aligned
+    dout = (double*)(((uintptr_t)dout + 7) & ~(uintptr_t)7);
+    CU(cudaMemcpyAsync(din, blocks, (size_t)n * 64 * 4, cudaMemcpyHostToDevice, c->stream));
+    { LaunchScope ls(c, K_DCT_SHIM); dct8x8_kernel<<<(n + 15) / 16, 128, 0, c->stream>>>(din, dout, n); }
+    CU(cudaMemcpyAsync(out, dout, (size_t)n * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    return icsp_sync(c);
+}
+
+int icsp_idct8x8(icsp_ctx* c, const int32_t* blocks, int n, int table, double* out)
+{
+    if (!c || !blocks || !out || n <= 0 || (table != 0 && table != 1)) return fail(c, ICSP_ERR_PARAM, "icsp_idct8x8: bad arguments");
+    CU(cudaSetDevice(c->device));
+    int rc = shim_reserve(c, (size_t)n * 64 * 12 + 16);
+    if (rc) return rc;
+    int32_t* din = (int32_t*)c->d_shim;
+    double* dout = (double*)(((uintptr_t)((char*)c->d_shim + (size_t)n * 64 * 4) + 7) & ~(uintptr_t)7);
+    CU(cudaMemcpyAsync(din, blocks, (size_t)n * 64 * 4, cudaMemcpyHostToDevice, c->stream));
+    {
+        LaunchScope ls(c, K_IDCT_SHIM);
+        if (table == 0) idct8x8_kernel<0><<<(n + 15) / 16, 128, 0, c->stream>>>(din, dout, n);
+        else idct8x8_kernel<1><<<(n + 15) / 16, 128, 0, c->stream>>>(din, dout, n);
+    }
+    CU(cudaMemcpyAsync(out, dout, (size_t)n * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    return icsp_sync(c);
+}
+
+// ---- instrumentation -------------------------------------------------------------------------------------
+int icsp_set_profiling(icsp_ctx* c, int enabled)
+{
+    if (!c) return ICSP_ERR_PARAM;
+    cudaSetDevice(c->device);
+    fold_pending(c);
+    c->profiling = enabled != 0;
+    return ICSP_OK;
+}
+int icsp_reset_stats(icsp_ctx* c)
+{
+    if (!c) return ICSP_ERR_PARAM;
+    cudaSetDevice(c->device);
+    fold_pending(c);
+    for (int k = 0; k < K_COUNT; k++) { c->total_ms[k] = 0; c->count[k] = 0; }
+    c->launches = 0;
+    return ICSP_OK;
+}
+int icsp_get_stats(icsp_ctx* c, icsp_kernel_stat* stats, int cap)
+{
+    if (!c || !stats || cap <= 0) return ICSP_ERR_PARAM;
+    cudaSetDevice(c->device);
+    fold_pending(c);
+    int n = 0;
+    for (int k = 0; k < K_COUNT && n < cap; k++) {
+        if (!c->count[k]) continue;
+        snprintf(stats[n].name, sizeof(stats[n].name), "%s", kKernelNames[k]);
+        stats[n].launches = c->count[k];
+        stats[n].total_ms = c->total_ms[k];
+        n++;
+    }
+    return n;
+}
+uint64_t icsp_launch_count(const icsp_ctx* c) { return c ? c->launches : 0; }
+
+int icsp_event_record(icsp_ctx* c, int slot)
+{
+    if (!c || slot < 0 || slot >= 8) return ICSP_ERR_PARAM;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->slots[slot], c->stream));
+    return ICSP_OK;
+}
+int icsp_event_elapsed_ms(icsp_ctx* c, int a, int b, float* ms)
+{
+    if (!c || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return ICSP_ERR_PARAM;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->slots[b]));
+    CU(cudaEventElapsedTime(ms, c->slots[a], c->slots[b]));
+    return ICSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+/* libicspcuda — B200 (sm_100a) implementation of ICSPCodec's per-frame data-parallel core, behind a C ABI.
+ *
+ * The reference (JawThrow/ICSPCodec) has no plugin/FFI interface; the seam this library replaces is the
+ * set of per-frame functions its frame loops call:
+ *
+ *   encoder  intraPrediction(FrameData&,int,int)              ICSP_Codec_Encoder.h:249   (ENC:556-643)
+ *            allintraPrediction(FrameData*,int,int,int)       ICSP_Codec_Encoder.h:250   (ENC:446-555)
+ *            interPrediction(FrameData&,FrameData&,int,int)   ICSP_Codec_Encoder.h:265   (ENC:1986-2072)
+ *            called from single_thread_encoding (ENC:217-245) and encoding_thread (ENC:186-213)
+ *   decoder  intraPredictionDecode / interPredictionDecode / allintraPredictionDecode
+ *                                                             ICSP_Codec_Decoder.h:201-202,212 (DEC:2083-2272)
+ *            called from IcspCodec::decoding (ICSP_Codec_Decoder.h:290-313)
+ *
+ * What those functions leave behind for the host — the fields intraBody/interBody (ENC:5032-5236) and the
+ * next frame read — is returned here as caller-owned SoA arrays (below) instead of the reference's
+ * per-block heap objects.  Plain pointers and sizes only; no C++/torch types.  All entry points return
+ * ICSP_OK (0) or a negative error code and never exit the process (the reference exit(-1)s, ENC:64-81).
+ *
+ * Geometry: width and height multiples of 16.  nmb = (width/16)*(height/16);  fb = width*height*3/2.
+ * Frames are planar I420 (Y, Cb, Cr).  A "GOP" is gop_len consecutive frames: 1 intra frame followed by
+ * gop_len-1 inter frames, closed (README.md:152, ICSP_thread.cpp:39-77).  gop_len == 1 means all-intra.
+ *
+ * SoA layout (n = number of frames in the call, frame index f = gop*gop_len + t):
+ *   levels  int16 [n][nmb][6][64]  blocks in bitstream order Y0,Y1,Y2,Y3,Cb,Cr; coefficients in zig-zag order
+ *                                  (ENC:3031-3094); element 0 is the DC level AFTER DC-DPCM (what DCentropy codes)
+ *   acflag  uint8 [n][nmb][6]      1 iff all 63 AC levels are zero (ENC:2784-2792)
+ *   mpm     uint8 [n][nmb][4]      MPMFlag        (intra frames; 0 on inter frames)        ENC:5057
+ *   ipm     uint8 [n][nmb][4]      intraPredMode  (intra frames; 0 on inter frames)        ENC:5058
+ *   mvd     int16 [n][nmb][2]      differential motion vector x,y as coded (inter frames)  ENC:5154
+ *   mv      int16 [n][nmb][2]      full motion vector (= Reconstructedmv)                  ENC:2145-2146
+ *   minsad  int32 [n][nmb]         SAD of the selected candidate
+ *   recon   uint8 [n][fb]          reconstructed I420 frame (reconstructedY/Cb/Cr; test_yuv.yuv ENC:6376-6421)
+ *
+ * Threading: a context is single-threaded; use one context per GPU per host thread.  Work is issued on the
+ * context's own CUDA stream; *_async entry points return before completion, icsp_sync() waits.
+ */
+#ifndef ICSPCUDA_H
+#define ICSPCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICSP_OK 0
+#define ICSP_ERR_PARAM (-1)   /* bad argument / geometry */
+#define ICSP_ERR_CUDA (-2)    /* CUDA runtime error (see icsp_last_error) */
+#define ICSP_ERR_NOMEM (-3)   /* device or pinned-host allocation failed */
+#define ICSP_ERR_CAPACITY (-4) /* more frames than the context was created for */
+
+typedef struct icsp_ctx icsp_ctx;
+
+typedef struct icsp_enc_out {     /* any pointer may be NULL: that array is not copied back */
+    int16_t* levels;
+    uint8_t* acflag;
+    uint8_t* mpm;
+    uint8_t* ipm;
+    int16_t* mvd;
+    int16_t* mv;
+    int32_t* minsad;
+    uint8_t* recon;
+} icsp_enc_out;
+
+typedef struct icsp_dec_in {      /* what the host bit reader parsed (DEC:38-404), same SoA layout */
+    const int16_t* levels;
+    const uint8_t* mpm;
+    const uint8_t* ipm;
+    const int16_t* mvd;
+} icsp_dec_in;
+
+/* ---- lifetime ----------------------------------------------------------------------------------- */
+int icsp_create(icsp_ctx** ctx, int device, int width, int height, int max_frames);
+void icsp_destroy(icsp_ctx* ctx);
+const char* icsp_last_error(const icsp_ctx* ctx);   /* ctx may be NULL: returns the create-time error */
+const char* icsp_version(void);
+int icsp_sync(icsp_ctx* ctx);
+
+/* Page-locked host memory for the SoA arrays / frames (fast, truly asynchronous H2D/D2H). Plain malloc'd
+ * buffers are accepted everywhere too; they are just slower to copy. */
+void* icsp_host_alloc(size_t bytes);
+void icsp_host_free(void* p);
+
+/* ---- encoder: replaces intraPrediction / interPrediction over a batch of closed GOPs -------------- */
+/* One call = H2D of the frames, the whole GOP batch on the GPU, D2H of the requested outputs, sync.
+ * Step t of the schedule processes frame t of EVERY GOP in one set of launches. */
+int icsp_encode_gops(icsp_ctx* ctx, const uint8_t* i420_frames, int n_gops, int gop_len, int qp_dc, int qp_ac,
+                     const icsp_enc_out* out);
+/* The same, split so that inputs can stay resident in HBM (bench "value" leg, multi-pass tools). */
+int icsp_enc_upload(icsp_ctx* ctx, const uint8_t* i420_frames, int n_frames);                 /* async H2D */
+int icsp_enc_run(icsp_ctx* ctx, int n_gops, int gop_len, int qp_dc, int qp_ac);               /* async */
+int icsp_enc_download(icsp_ctx* ctx, int n_frames, const icsp_enc_out* out);                  /* async D2H */
+
+/* ---- decoder: replaces intraPredictionDecode / interPredictionDecode (double cosine table) -------- */
+int icsp_decode_gops(icsp_ctx* ctx, const icsp_dec_in* in, int n_gops, int gop_len, int qp_dc, int qp_ac,
+                     uint8_t* i420_out);
+int icsp_dec_upload(icsp_ctx* ctx, const icsp_dec_in* in, int n_frames);
+int icsp_dec_run(icsp_ctx* ctx, int n_gops, int gop_len, int qp_dc, int qp_ac);
+int icsp_dec_download(icsp_ctx* ctx, int n_frames, uint8_t* i420_out);
+
+/* ---- kernel-level shims (unit parity + micro-benchmarks); host pointers, synchronous ---------------- */
+/* motionEstimation (ENC:2073-2155): n frame pairs, luma planes only [n][w*h]; carried spiral state per frame */
+int icsp_me_sad(icsp_ctx* ctx, const uint8_t* cur_y, const uint8_t* ref_y, int n, int16_t* mv, int32_t* minsad);
+/* DCT_block (ENC:2685-2749): int32 [n][64] -> f64 [n][64] */
+int icsp_dct8x8(icsp_ctx* ctx, const int32_t* blocks, int n, double* out);
+/* IDCT_block (ENC:2825-2893 when table==0, DEC:3331-3445 when table==1): int32 [n][64] -> f64 [n][64] */
+int icsp_idct8x8(icsp_ctx* ctx, const int32_t* blocks, int n, int table, double* out);
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+/* When enabled every kernel launch is bracketed by CUDA events on the context stream. */
+#define ICSP_MAX_KERNELS 24
+typedef struct icsp_kernel_stat {
+    char name[40];
+    uint64_t launches;
+    double total_ms;
+} icsp_kernel_stat;
+int icsp_set_profiling(icsp_ctx* ctx, int enabled);
+int icsp_reset_stats(icsp_ctx* ctx);
+int icsp_get_stats(icsp_ctx* ctx, icsp_kernel_stat* stats, int cap);   /* returns number of entries, syncs */
+uint64_t icsp_launch_count(const icsp_ctx* ctx);                       /* kernels launched since create/reset */
+/* Event timing on the context stream: record slot a, do work, record slot b, elapsed(a,b) after icsp_sync. */
+int icsp_event_record(icsp_ctx* ctx, int slot);                        /* slot in [0,8) */
+int icsp_event_elapsed_ms(icsp_ctx* ctx, int slot_a, int slot_b, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICSPCUDA_H */
