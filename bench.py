@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — CIF encode throughput of the ICSPCodec hot path on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[3] — a batch of 64 independent synthetic CIF streams x 300 frames,
+-q 8, --intraPeriod 10 (1 920 closed GOPs of 10 frames = 19 200 frames per GPU).  One *step* = one pass of the
+hot path over that whole batch (intra wavefront, ME/MC, DCT/quant, DC-DPCM, IDCT/recon for every frame).
+Multi-GPU: GOPs share no state, so every rank encodes its own 64 streams (weak scaling, no collective).
+
+  value  frames/s, whole job, inputs already resident in HBM, timed with CUDA events on the library stream
+  e2e    frames/s through icsp_encode_gops() with pinned HOST buffers (H2D of the frames, kernels, D2H of every
+         syntax array + the reconstruction inside the timed region)
+  roofline / kernels   per-kernel CUDA-event times measured live during the timed steps
+  cpu_baseline         the compiled reference (oracle/_ref) --EnMultiThread on the host cores, bounded sample
+
+`--impl reference` times the reference's own CPU encoder (all host threads) on a bounded sample of the same
+workload and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 352, 288
+FB = W * H * 3 // 2
+NMB = 396
+METRIC = "cif_encode_frames_per_s"
+UNIT = "frames/s"
+
+
+def peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- workload ---------------------------------------------------------------------------------------------
+def make_batch(streams: int, frames: int, rank: int, unique: int = 8) -> np.ndarray:
+    """[streams*frames][FB] uint8: `unique` seeded high-motion clips (seeds 1000+i); every
+    further stream reuses one of them with a stream-specific circular shift so that no two streams are identical."""
+    from icspcodec_b200 import synth
+    unique = min(unique, streams)
+    base = [synth.make_clip("highmotion", frames, 1000 + 64 * rank + i) for i in range(unique)]
+    out = np.empty((streams, frames, FB), np.uint8)
+    for s in range(streams):
+        src = base[s % unique]
+        k = s // unique
+        if k == 0:
+            out[s] = src
+            continue
+        y = src[:, : W * H].reshape(frames, H, W)
+        cb = src[:, W * H: W * H + W * H // 4].reshape(frames, H // 2, W // 2)
+        cr = src[:, W * H + W * H // 4:].reshape(frames, H // 2, W // 2)
+        out[s, :, : W * H] = np.roll(y, (6 * k, 10 * k), axis=(1, 2)).reshape(frames, -1)
+        out[s, :, W * H: W * H + W * H // 4] = np.roll(cb, (3 * k, 5 * k), axis=(1, 2)).reshape(frames, -1)
+        out[s, :, W * H + W * H // 4:] = np.roll(cr, (3 * k, 5 * k), axis=(1, 2)).reshape(frames, -1)
+    return out.reshape(streams * frames, FB)
+
+
+# ---- clocks -----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows: list[list[str]] = []
+        self.proc = None
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t = threading.Thread(target=self._pump, daemon=True)
+        self.t.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load = upper half of the clock samples (the sampler also sees the idle gaps between steps)
+        load = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU reference arm --------------------------------------------------------------------------------------
+def ref_binary() -> str | None:
+    p = os.path.join(ROOT, "oracle", "_ref", "ICSPCodec_O2")
+    return p if os.path.exists(p) else None
+
+
+def run_reference_sample(n_proc: int, threads: int, frames: int, clips: list[np.ndarray]) -> float:
+    """Encode `n_proc` streams concurrently with the unmodified reference CLI (--EnMultiThread threads each).
+    Returns wall seconds for the whole sample (process start to exit, like the README's timings)."""
+    exe = ref_binary()
+    tmp = tempfile.mkdtemp(prefix="icspbench_")
+    try:
+        dirs = []
+        for i in range(n_proc):
+            d = os.path.join(tmp, f"p{i}")
+            os.makedirs(d)
+            clips[i % len(clips)].tofile(os.path.join(d, "clip_cif.yuv"))
+            dirs.append(d)
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([exe, "-i", "clip_cif.yuv", "-n", str(frames), "-q", "8", "--intraPeriod", "10",
+                                   "--EnMultiThread", str(threads)], cwd=d, stdout=subprocess.DEVNULL) for d in dirs]
+        for p in procs:
+            if p.wait() != 0:
+                raise RuntimeError("reference encoder failed")
+        return time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def oracle_port_sample(frames_arr: np.ndarray) -> float:
+    from oracle import oracle_py as O
+    t0 = time.perf_counter()
+    O.encode(frames_arr, W, H, 8, 8, 10)
+    return time.perf_counter() - t0
+
+
+def cpu_plan(frames: int):
+    cores = os.cpu_count() or 1
+    threads = min(8, cores)
+    n_proc = max(1, cores // threads)
+    return cores, threads, n_proc
+
+
+def reference_arm(args) -> dict:
+    from icspcodec_b200 import synth
+    frames = args.frames
+    cores, threads, n_proc = cpu_plan(frames)
+    n_proc = min(n_proc, args.streams)
+    clips = [synth.make_clip("highmotion", frames, 1000 + i) for i in range(min(n_proc, 4))]
+    times = []
+    if ref_binary():
+        kind = "reference"
+        sample = (f"{n_proc} streams x {frames} frames per step, one unmodified reference process per stream "
+                  f"(g++ -O2, --EnMultiThread {threads}; MT mode reconstructs but writes no bitstream, ICSP_thread.cpp:76)")
+        for i in range(args.warmup + args.steps):
+            t = run_reference_sample(n_proc, threads, frames, clips)
+            if i >= args.warmup:
+                times.append(t)
+        used = min(cores, n_proc * threads)
+    else:
+        kind = "port"
+        n_proc, used = 1, 1
+        sample = f"1 stream x {min(frames, 60)} frames per step, oracle/icsp_oracle.c single thread (oracle/_ref not built)"
+        frames = min(frames, 60)
+        for i in range(args.warmup + args.steps):
+            t = oracle_port_sample(clips[0][:frames])
+            if i >= args.warmup:
+                times.append(t)
+    total = float(sum(times))
+    value = n_proc * frames * len(times) / total
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64+u8", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def workload_config(args) -> dict:
+    return {"workload": f"BASELINE configs[3]: batch of {args.streams} synthetic high-motion CIF 352x288 I420 streams x {args.frames} frames per GPU, "
+                        f"-q 8, --intraPeriod 10 ({args.streams * args.frames // 10} closed GOPs per GPU, GOP-sharded, no collective)",
+            "streams_per_gpu": args.streams, "frames_per_stream": args.frames, "qp": 8, "intra_period": 10,
+            "l2": "inputs (2.9 GB/GPU) and outputs (8.9 GB/GPU) are far larger than the 126 MB L2; no flush needed"}
+
+
+# ---- our arm ------------------------------------------------------------------------------------------------
+ALG_BYTES = {  # algorithmic HBM bytes per frame each kernel must move (DESIGN.md "Kernels")
+    "me_sad_kernel": 2 * W * H + NMB * 8,                                    # cur Y + ref Y + mv + minsad
+    "fdct_quant_kernel": 2 * FB + NMB * 6 * (128 + 1 + 8),                   # cur + ref -> levels, acflag, raw DC
+    "idct_recon_kernel<enc>": NMB * 6 * (128 + 4) + FB + FB,                 # levels, DC + ref -> recon
+    "intra_luma_kernel<enc>": 2 * W * H + NMB * 4 * (128 + 3),               # cur Y -> recon Y, levels, flags
+    "dc_chain_kernel": NMB * 6 * (8 + 4 + 2) + NMB * 8,
+}
+
+
+def ours(args) -> dict | None:
+    import torch
+    import torch.distributed as dist
+    from icspcodec_b200 import IcspCuda, build
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libicspcuda has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_gops = args.streams * args.frames // 10
+    n = n_gops * 10
+    batch = make_batch(args.streams, args.frames, rank)[:n]
+    ctx = IcspCuda(W, H, max_frames=n, device=local)
+    from icspcodec_b200 import PinnedArray
+    pin_in = PinnedArray((n, FB), np.uint8)
+    pin_in.array[:] = batch
+    del batch
+    res = ctx.alloc_result(n, pinned=True)
+    e2e_fields = ("levels", "acflag", "mpm", "ipm", "mvd", "recon")
+
+    # ---- value: inputs resident in HBM --------------------------------------------------------------------
+    ctx.upload(pin_in.array)
+    ctx.sync()
+    for _ in range(args.warmup):
+        ctx.run(n_gops, 10, 8, 8)
+    ctx.sync()
+    sampler = ClockSampler(local)
+    ctx.set_profiling(True)
+    ctx.reset_stats()
+    barrier()
+    sampler.start()
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        ctx.run(n_gops, 10, 8, 8)
+    ctx.event_record(1)
+    ctx.sync()
+    barrier()
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    clocks = sampler.stop()
+    launches = ctx.launch_count()
+    stats = ctx.stats()
+    ctx.set_profiling(False)
+
+    # ---- e2e: host buffers, H2D + kernels + D2H inside the timed region ---------------------------------------
+    ctx.encode_gops(pin_in.array, n_gops, 10, 8, 8, out=res, fields=e2e_fields)   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.encode_gops(pin_in.array, n_gops, 10, 8, 8, out=res, fields=e2e_fields)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = n * FB
+    d2h = sum(getattr(res, f).nbytes for f in e2e_fields)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+
+    value = world * n * args.steps / (dev_ms / 1e3)
+    e2e_value = world * n * args.e2e_steps / (e2e_ms / 1e3)
+    peak, peak_src = peaks()
+    kernels = {}
+    p_frames = n_gops * 9 * args.steps
+    i_frames = n_gops * args.steps
+    for name, s in stats.items():
+        if s["launches"] == 0:
+            continue
+        frames_k = i_frames if name.startswith("intra_luma") else (p_frames if name.startswith("me_") else p_frames + i_frames)
+        ent = {"launches": s["launches"], "total_ms": round(s["total_ms"], 3), "avg_ms": round(s["total_ms"] / s["launches"], 4),
+               "share": round(s["total_ms"] / max(1e-9, sum(x["total_ms"] for x in stats.values())), 4)}
+        if name in ALG_BYTES and s["total_ms"] > 0:
+            gbs = ALG_BYTES[name] * frames_k / (s["total_ms"] * 1e-3) / 1e9
+            ent["alg_GBps"] = round(gbs, 1)
+            ent["hbm_frac"] = round(gbs / peak, 4)
+        if name == "me_sad_kernel" and s["total_ms"] > 0:
+            ent["Gpos_per_s"] = round(p_frames * NMB * 64 / (s["total_ms"] * 1e-3) / 1e9, 2)
+        kernels[name] = ent
+    dom = max(kernels, key=lambda k: kernels[k]["total_ms"])
+    d = kernels[dom]
+    per_launch_frames = n_gops
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": d.get("alg_GBps"), "peak": peak, "unit": "GB/s",
+                "frac": d.get("hbm_frac"), "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": ALG_BYTES.get(dom, 0) * per_launch_frames, "avg_launch_ms": d["avg_ms"],
+                "note": "FP64-issue bound for the DCT/IDCT kernels (strict no-FMA binary64, SURVEY §8d); HBM fraction reported as the contract asks"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64+u8", "data": "synthetic (8 seeded high-motion clips per GPU, each reused 8x with a stream-specific circular shift)",
+            "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps},
+            "roofline": roofline, "kernels": kernels,
+            "me_sad_Gpos_per_s": kernels.get("me_sad_kernel", {}).get("Gpos_per_s")}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    return line
+
+
+def cpu_baseline(args) -> dict:
+    from icspcodec_b200 import synth
+    cores, threads, n_proc = cpu_plan(args.frames)
+    n_proc = min(n_proc, args.streams)
+    clips = [synth.make_clip("highmotion", args.frames, 1000 + i) for i in range(min(n_proc, 4))]
+    if ref_binary():
+        run_reference_sample(1, threads, min(args.frames, 30), clips)     # page the binary in
+        secs = run_reference_sample(n_proc, threads, args.frames, clips)
+        return {"value": n_proc * args.frames / secs, "unit": UNIT, "cores": min(cores, n_proc * threads), "kind": "reference",
+                "sample": f"{n_proc} streams x {args.frames} frames, one unmodified reference process per stream (g++ -O2, --EnMultiThread {threads}, "
+                          f"recon only: MT mode writes no bitstream), wall {secs:.2f} s on {cores} host cores"}
+    f = min(args.frames, 60)
+    secs = oracle_port_sample(clips[0][:f])
+    return {"value": f / secs, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"1 stream x {f} frames, oracle/icsp_oracle.c, 1 thread"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        print(json.dumps(reference_arm(args)), flush=True)
+        return
+    line = ours(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
