@@ -71,49 +71,60 @@ def make_batch(streams: int, frames: int, rank: int, unique: int = 8) -> np.ndar
 
 # ---- clocks -----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi sampler (B200_PROFILING.md clocks line).  Started before the warm-up so that it is already
+    streaming when the timed region begins; only samples whose timestamp falls inside [t0, t1] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows: list[list[str]] = []
+        self.rows: list[tuple[float, list[str]]] = []
         self.proc = None
 
     def start(self):
         if not shutil.which("nvidia-smi"):
             return
-        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         self.t = threading.Thread(target=self._pump, daemon=True)
         self.t.start()
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float, t1: float) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-                for nm, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
+
+        def collect(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                    for nm, v in zip(names, r[4:8]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+                except Exception:
+                    continue
+            return sm, mx, pw, reasons
+        inside = [x for x in self.rows if t0 <= x[0] <= t1 + 0.03]
+        sm, mx, pw, reasons = collect(inside)
+        where = "timed region"
+        if not sm:   # region shorter than the sampler period: fall back to every sample of the run
+            sm, mx, pw, reasons = collect(self.rows)
+            where = "whole run (timed region shorter than the sampling period)"
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # samples under load = upper half of the clock samples (the sampler also sees the idle gaps between steps)
-        load = sorted(sm)[len(sm) // 2:]
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "window": where, "reasons": sorted(reasons)}
 
 
 # ---- CPU reference arm --------------------------------------------------------------------------------------
@@ -137,10 +148,11 @@ def run_reference_sample(n_proc: int, threads: int, frames: int, clips: list[np.
         t0 = time.perf_counter()
         procs = [subprocess.Popen([exe, "-i", "clip_cif.yuv", "-n", str(frames), "-q", "8", "--intraPeriod", "10",
                                    "--EnMultiThread", str(threads)], cwd=d, stdout=subprocess.DEVNULL) for d in dirs]
-        for p in procs:
-            if p.wait() != 0:
-                raise RuntimeError("reference encoder failed")
-        return time.perf_counter() - t0
+        rcs = [p.wait() for p in procs]
+        dt = time.perf_counter() - t0
+        if any(rcs):
+            raise RuntimeError(f"reference encoder failed (exit codes {rcs})")
+        return dt
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -153,10 +165,11 @@ def oracle_port_sample(frames_arr: np.ndarray) -> float:
 
 
 def cpu_plan(frames: int):
-    cores = os.cpu_count() or 1
-    threads = min(8, cores)
-    n_proc = max(1, cores // threads)
-    return cores, threads, n_proc
+    """One reference process per host core, each in --EnMultiThread 1 mode.  (With >1 thread per process the
+    reference's job queue races — `while(!Q.empty())` is read outside the mutex, ENC:191-194 — and crashes at the
+    tail of the queue on many-core hosts; GOP-parallel threads and stream-parallel processes do the same work.)"""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return cores, 1, cores
 
 
 def reference_arm(args) -> dict:
@@ -242,24 +255,26 @@ def ours(args) -> dict | None:
     e2e_fields = ("levels", "acflag", "mpm", "ipm", "mvd", "recon")
 
     # ---- value: inputs resident in HBM --------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     ctx.upload(pin_in.array)
     ctx.sync()
     for _ in range(args.warmup):
         ctx.run(n_gops, 10, 8, 8)
     ctx.sync()
-    sampler = ClockSampler(local)
     ctx.set_profiling(True)
     ctx.reset_stats()
     barrier()
-    sampler.start()
+    t_begin = time.time()
     ctx.event_record(0)
     for _ in range(args.steps):
         ctx.run(n_gops, 10, 8, 8)
     ctx.event_record(1)
     ctx.sync()
     barrier()
+    t_end = time.time()
     dev_ms = ctx.event_elapsed_ms(0, 1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     launches = ctx.launch_count()
     stats = ctx.stats()
     ctx.set_profiling(False)
@@ -321,7 +336,15 @@ def ours(args) -> dict | None:
             "roofline": roofline, "kernels": kernels,
             "me_sad_Gpos_per_s": kernels.get("me_sad_kernel", {}).get("Gpos_per_s")}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args)
+        try:
+            line["cpu_baseline"] = cpu_baseline(args)
+        except Exception as e:  # never lose the GPU numbers to a CPU-side failure
+            print(f"bench.py: reference baseline failed ({e}); falling back to the oracle port", file=sys.stderr)
+            from icspcodec_b200 import synth
+            f = min(args.frames, 60)
+            secs = oracle_port_sample(synth.make_clip("highmotion", f, 1000))
+            line["cpu_baseline"] = {"value": f / secs, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"1 stream x {f} frames, oracle/icsp_oracle.c, 1 thread (reference run failed: {e})"}
     return line
 
 
@@ -334,8 +357,8 @@ def cpu_baseline(args) -> dict:
         run_reference_sample(1, threads, min(args.frames, 30), clips)     # page the binary in
         secs = run_reference_sample(n_proc, threads, args.frames, clips)
         return {"value": n_proc * args.frames / secs, "unit": UNIT, "cores": min(cores, n_proc * threads), "kind": "reference",
-                "sample": f"{n_proc} streams x {args.frames} frames, one unmodified reference process per stream (g++ -O2, --EnMultiThread {threads}, "
-                          f"recon only: MT mode writes no bitstream), wall {secs:.2f} s on {cores} host cores"}
+                "sample": f"{n_proc} streams x {args.frames} frames, one unmodified reference process per stream (g++ -O2, --EnMultiThread {threads}: the "
+                          f"reference's GOP-job path, reconstruction only, no bitstream, ICSP_thread.cpp:76), wall {secs:.2f} s on {cores} host cores"}
     f = min(args.frames, 60)
     secs = oracle_port_sample(clips[0][:f])
     return {"value": f / secs, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"1 stream x {f} frames, oracle/icsp_oracle.c, 1 thread"}

@@ -427,12 +427,27 @@ __global__ void __launch_bounds__(IW_THREADS) intra_luma_kernel(Geom g, FramePtr
 }
 
 // =====================================================================================================
-// Motion estimation (R1, R2).  One CTA per macroblock row per frame: the current rows and the 48-row search
-// window of the previous reconstruction (apron built with clamp + the reference's zero last row/column) are
-// staged in shared memory with 16-byte loads; one warp per macroblock, two candidates per lane, packed-byte
-// SAD, ballot/shuffle winner selection reproducing visiting order, strict-< tie-break and the second-zero
-// early break.  `fixup` == 1 re-evaluates only macroblocks whose carried start state turned out != 0.
+// Motion estimation (R1, R2).  One CTA per macroblock-row segment (<= 22 MBs; a whole CIF row) per frame.
+// The 48-row search window of the previous reconstruction (apron = clamp + the reference's zero last
+// row/column, never materialised in HBM) and the 16 current rows are staged in shared memory with 16-byte
+// loads.  The window is kept in FOUR byte-shifted copies so that every candidate row is word aligned in the
+// copy (16+dx)&3: the inner loop is 4 LDS.32 + 1 broadcast LDS.128 + 4 VABSDIFF4.ACC per row, no funnel shifts.
+// One warp per macroblock, two candidates per lane.  Row pitch == 8 (mod 32) words and copy offsets {0,1,1,1}
+// make the 64 state-0 candidates fall exactly two per bank, and c_slot assigns them to (round, lane) so that
+// both rounds are bank-conflict free.  Winner selection (redux.sync min) reproduces visiting order, strict-<
+// tie-break and the second-zero early break.  `fixup` re-evaluates MBs whose carried start state is != 0.
 // =====================================================================================================
+struct MeLayout {
+    int seg_mbs;   // macroblocks per segment
+    int nseg;      // segments per macroblock row
+    int row_w;     // valid words per window row = (seg_mbs*16 + 32)/4
+    int pitch_w;   // words per window row in shared memory, == 8 (mod 32)
+    int copy_w;    // words per copy = 48*pitch_w
+};
+__constant__ unsigned char c_slot[8][2][32];   // start state, round, lane -> visit index handled by that lane
+__host__ __device__ inline int me_copy_off(const MeLayout& L, int s) { return s * L.copy_w + (s ? 1 : 0); }
+__host__ __device__ inline size_t me_smem_bytes(const MeLayout& L) { return (size_t)(4 * L.copy_w + 8) * 4 + (size_t)16 * L.seg_mbs * 16; }
+
 __device__ __forceinline__ uint4 window_chunk(const uint8_t* __restrict__ plane, int w, int h, int py, int pxc)
 {   // 16 bytes of the padded image (pad 16) at padded row py, padded columns [16*pxc, 16*pxc+16)
     const int PH = h + 32, PW = w + 32;
@@ -449,85 +464,100 @@ __device__ __forceinline__ uint4 window_chunk(const uint8_t* __restrict__ plane,
     return o;
 }
 
-__global__ void __launch_bounds__(1024) me_sad_kernel(Geom g, FramePtrs p, Step st, int fixup)
+// stage window (copy 0, and the shifted copies when SHIFTED) + current rows of segment (mby, seg)
+template <bool SHIFTED>
+__device__ __forceinline__ void me_stage(const Geom& g, const MeLayout& L, uint32_t* s_win, uint8_t* s_cur,
+                                         const uint8_t* __restrict__ cury, const uint8_t* __restrict__ refy, int mby, int m0, int nmbs)
+{
+    const int chunks = nmbs + 2;
+    for (int i = threadIdx.x; i < 48 * chunks; i += blockDim.x) {
+        const int row = i / chunks, c = i - row * chunks;
+        *(uint4*)(s_win + row * L.pitch_w + c * 4) = window_chunk(refy, g.w, g.h, mby * 16 + row, m0 + c);
+    }
+    for (int i = threadIdx.x; i < 16 * nmbs; i += blockDim.x) {
+        const int row = i / nmbs, c = i - row * nmbs;
+        *(uint4*)(s_cur + (row * L.seg_mbs + c) * 16) = __ldg((const uint4*)(cury + (size_t)(mby * 16 + row) * g.w + (m0 + c) * 16));
+    }
+    __syncthreads();
+    if (SHIFTED) {
+        const int rw = chunks * 4;
+        for (int i = threadIdx.x; i < 48 * rw; i += blockDim.x) {
+            const int row = i / rw, c = i - row * rw;
+            const uint32_t a = s_win[row * L.pitch_w + c], b = (c + 1 < rw) ? s_win[row * L.pitch_w + c + 1] : 0u;
+#pragma unroll
+            for (int sft = 1; sft < 4; sft++) s_win[me_copy_off(L, sft) + row * L.pitch_w + c] = __funnelshift_r(a, b, 8 * sft);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fixup)
 {
     extern __shared__ __align__(16) unsigned char s_me[];
-    const int gop = blockIdx.y, mby = blockIdx.x;
+    const int gop = blockIdx.y, mby = blockIdx.x / L.nseg, seg = blockIdx.x - mby * L.nseg;
+    const int m0 = seg * L.seg_mbs, nmbs = min(L.seg_mbs, g.mbw - m0);
     const size_t f = (size_t)gop * st.gop_len + st.t;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const uint8_t* states = p.mestate + (size_t)gop * g.nmb + mby * g.mbw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint8_t* states = p.mestate + (size_t)gop * g.nmb + mby * g.mbw + m0;
     if (fixup) {
         if (p.meflag[gop] == 0) return;
         int any = 0;
-        for (int i = threadIdx.x; i < g.mbw; i += blockDim.x) any |= states[i];
+        for (int i = threadIdx.x; i < nmbs; i += blockDim.x) any |= states[i];
         if (!__syncthreads_or(any)) return;
     }
-    const int pitch = g.w + 32;                 // bytes per window row
-    uint8_t* s_win = s_me;                      // [48][pitch]
-    uint8_t* s_cur = s_me + 48 * pitch;         // [16][w]
-    const uint8_t* cury = p.cur + f * g.fb;
-    const uint8_t* refy = p.rec + (f - 1) * g.fb;
-    const int chunks = pitch / 16;
-    for (int i = threadIdx.x; i < 48 * chunks; i += blockDim.x) {
-        const int row = i / chunks, c = i - row * chunks;
-        *(uint4*)(s_win + row * pitch + c * 16) = window_chunk(refy, g.w, g.h, mby * 16 + row, c);
-    }
-    for (int i = threadIdx.x; i < 16 * (g.w / 16); i += blockDim.x) {
-        const int row = i / (g.w / 16), c = i - row * (g.w / 16);
-        *(uint4*)(s_cur + row * g.w + c * 16) = __ldg((const uint4*)(cury + (size_t)(mby * 16 + row) * g.w + c * 16));
-    }
-    __syncthreads();
+    uint32_t* s_win = (uint32_t*)s_me;
+    uint8_t* s_cur = s_me + (size_t)(4 * L.copy_w + 8) * 4;
+    me_stage<true>(g, L, s_win, s_cur, p.cur + f * g.fb, p.rec + (f - 1) * g.fb, mby, m0, nmbs);
+    if (warp >= nmbs) return;
+    const int mbl = warp;
+    const int state = fixup ? states[mbl] : 0;
+    if (fixup && state == 0) return;
 
-    for (int mbx = warp; mbx < g.mbw; mbx += nwarps) {
-        const int state = fixup ? states[mbx] : 0;
-        if (fixup && state == 0) continue;
-        uint32_t sad[2];
+    uint32_t sad[2];
+    int vidx[2];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; h2++) {
-            const int idx = lane + 32 * h2;
-            const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
-            const int col = mbx * 16 + 16 + dx;          // padded column of the candidate's first pixel
-            const uint32_t* wrow = (const uint32_t*)(s_win + (16 + dy) * pitch + (col & ~3));
-            const int sh = (col & 3) * 8;
-            const uint32_t* crow = (const uint32_t*)(s_cur + mbx * 16);
-            uint32_t acc = 0;
-#pragma unroll 4
-            for (int j = 0; j < 16; j++) {
-                const uint32_t w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3], w4 = wrow[4];
-                acc = __vsadu4(__funnelshift_r(w0, w1, sh), crow[0]) + acc;
-                acc = __vsadu4(__funnelshift_r(w1, w2, sh), crow[1]) + acc;
-                acc = __vsadu4(__funnelshift_r(w2, w3, sh), crow[2]) + acc;
-                acc = __vsadu4(__funnelshift_r(w3, w4, sh), crow[3]) + acc;
-                wrow += pitch / 4;
-                crow += g.w / 4;
-            }
-            sad[h2] = acc;
+    for (int rnd = 0; rnd < 2; rnd++) {
+        const int idx = c_slot[state][rnd][lane];
+        const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
+        const int col = mbl * 16 + 16 + dx;   // window byte column of the candidate's first pixel
+        const uint32_t* wrow = s_win + me_copy_off(L, col & 3) + (16 + dy) * L.pitch_w + (col >> 2);
+        const uint4* crow = (const uint4*)(s_cur + mbl * 16);
+        uint32_t acc = 0;
+#pragma unroll 8
+        for (int j = 0; j < 16; j++) {
+            const uint4 c = *crow;
+            acc = __vsadu4(wrow[0], c.x) + acc;
+            acc = __vsadu4(wrow[1], c.y) + acc;
+            acc = __vsadu4(wrow[2], c.z) + acc;
+            acc = __vsadu4(wrow[3], c.w) + acc;
+            wrow += L.pitch_w;
+            crow += L.seg_mbs;
         }
-        // zero-SAD visits in visiting order; the search breaks at the SECOND one (ENC:2130-2141)
-        const unsigned long long z = (unsigned long long)__ballot_sync(0xffffffffu, sad[0] == 0) |
-                                     ((unsigned long long)__ballot_sync(0xffffffffu, sad[1] == 0) << 32);
-        int win, moves = 64;
-        uint32_t best;
-        if (__popcll(z) >= 2) {
-            win = __ffsll((long long)(z & (z - 1))) - 1;
-            moves = win + 1;
-            best = 0;
-        } else {   // first visited minimum: min over key = SAD*64 + visit index
-            uint32_t key = min(sad[0] * 64u + lane, sad[1] * 64u + lane + 32u);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
-            win = key & 63; best = key >> 6;
-        }
-        if (lane == 0) {
-            const int mb = mby * g.mbw + mbx;
-            // mv = MB origin - best position (ENC:2145-2146)
-            p.mv[(f * g.nmb + mb) * 2] = (int16_t)(-c_cand[state][win][0]);
-            p.mv[(f * g.nmb + mb) * 2 + 1] = (int16_t)(-c_cand[state][win][1]);
-            p.minsad[f * g.nmb + mb] = (int32_t)best;
-            if (!fixup) {
-                p.memoves[(size_t)gop * g.nmb + mb] = (uint8_t)moves;
-                if (moves < 64) atomicAdd(&p.meflag[gop], 1u);
-            }
+        sad[rnd] = acc;
+        vidx[rnd] = idx;
+    }
+    // the search breaks at the SECOND zero-SAD visit (ENC:2130-2141); otherwise the first visited minimum wins
+    const unsigned zk0 = sad[0] == 0 ? (unsigned)vidx[0] : 64u, zk1 = sad[1] == 0 ? (unsigned)vidx[1] : 64u;
+    const unsigned z1 = __reduce_min_sync(0xffffffffu, min(zk0, zk1));
+    int win = -1, moves = 64;
+    uint32_t best = 0;
+    if (z1 < 64u) {
+        const unsigned z2 = __reduce_min_sync(0xffffffffu, min(zk0 > z1 ? zk0 : 64u, zk1 > z1 ? zk1 : 64u));
+        if (z2 < 64u) { win = (int)z2; moves = win + 1; }
+    }
+    if (win < 0) {
+        const unsigned key = __reduce_min_sync(0xffffffffu, min(sad[0] * 64u + vidx[0], sad[1] * 64u + vidx[1]));
+        win = key & 63; best = key >> 6;
+    }
+    if (lane == 0) {
+        const int mb = mby * g.mbw + m0 + mbl;
+        // mv = MB origin - best position (ENC:2145-2146)
+        p.mv[(f * g.nmb + mb) * 2] = (int16_t)(-c_cand[state][win][0]);
+        p.mv[(f * g.nmb + mb) * 2 + 1] = (int16_t)(-c_cand[state][win][1]);
+        p.minsad[f * g.nmb + mb] = (int32_t)best;
+        if (!fixup) {
+            p.memoves[(size_t)gop * g.nmb + mb] = (uint8_t)moves;
+            if (moves < 64) atomicAdd(&p.meflag[gop], 1u);
         }
     }
 }
@@ -535,53 +565,42 @@ __global__ void __launch_bounds__(1024) me_sad_kernel(Geom g, FramePtrs p, Step 
 // Exact fallback, pass 1: for frames where some search broke early, find for every macroblock and every one of
 // the 8 possible start states which visits have SAD == 0 (block identical to the candidate).  The break point
 // of a search depends only on these masks, never on non-zero SAD values.
-__global__ void __launch_bounds__(1024) me_zero_kernel(Geom g, FramePtrs p, Step st)
+__global__ void __launch_bounds__(704) me_zero_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
 {
     extern __shared__ __align__(16) unsigned char s_me[];
-    const int gop = blockIdx.y, mby = blockIdx.x;
+    const int gop = blockIdx.y, mby = blockIdx.x / L.nseg, seg = blockIdx.x - mby * L.nseg;
     if (p.meflag[gop] == 0) return;
+    const int m0 = seg * L.seg_mbs, nmbs = min(L.seg_mbs, g.mbw - m0);
     const size_t f = (size_t)gop * st.gop_len + st.t;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int pitch = g.w + 32;
-    uint8_t* s_win = s_me;
-    uint8_t* s_cur = s_me + 48 * pitch;
-    const uint8_t* cury = p.cur + f * g.fb;
-    const uint8_t* refy = p.rec + (f - 1) * g.fb;
-    const int chunks = pitch / 16;
-    for (int i = threadIdx.x; i < 48 * chunks; i += blockDim.x) {
-        const int row = i / chunks, c = i - row * chunks;
-        *(uint4*)(s_win + row * pitch + c * 16) = window_chunk(refy, g.w, g.h, mby * 16 + row, c);
-    }
-    for (int i = threadIdx.x; i < 16 * (g.w / 16); i += blockDim.x) {
-        const int row = i / (g.w / 16), c = i - row * (g.w / 16);
-        *(uint4*)(s_cur + row * g.w + c * 16) = __ldg((const uint4*)(cury + (size_t)(mby * 16 + row) * g.w + c * 16));
-    }
-    __syncthreads();
-    for (int mbx = warp; mbx < g.mbw; mbx += nwarps) {
-        for (int state = 0; state < 8; state++) {
-            unsigned long long z = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* s_win = (uint32_t*)s_me;
+    uint8_t* s_cur = s_me + (size_t)(4 * L.copy_w + 8) * 4;
+    me_stage<false>(g, L, s_win, s_cur, p.cur + f * g.fb, p.rec + (f - 1) * g.fb, mby, m0, nmbs);
+    if (warp >= nmbs) return;
+    const int mbl = warp;
+    for (int state = 0; state < 8; state++) {
+        unsigned long long z = 0;
 #pragma unroll
-            for (int h2 = 0; h2 < 2; h2++) {
-                const int idx = lane + 32 * h2;
-                const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
-                const int col = mbx * 16 + 16 + dx;
-                const uint32_t* wrow = (const uint32_t*)(s_win + (16 + dy) * pitch + (col & ~3));
-                const int sh = (col & 3) * 8;
-                const uint32_t* crow = (const uint32_t*)(s_cur + mbx * 16);
-                uint32_t diff = 0;
-                for (int j = 0; j < 16 && diff == 0; j++) {   // early out on the first differing row
-                    const uint32_t w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3], w4 = wrow[4];
-                    diff |= __funnelshift_r(w0, w1, sh) ^ crow[0];
-                    diff |= __funnelshift_r(w1, w2, sh) ^ crow[1];
-                    diff |= __funnelshift_r(w2, w3, sh) ^ crow[2];
-                    diff |= __funnelshift_r(w3, w4, sh) ^ crow[3];
-                    wrow += pitch / 4;
-                    crow += g.w / 4;
-                }
-                z |= (unsigned long long)__ballot_sync(0xffffffffu, diff == 0) << (32 * h2);
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int idx = lane + 32 * h2;
+            const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
+            const int col = mbl * 16 + 16 + dx;
+            const uint32_t* wrow = s_win + (16 + dy) * L.pitch_w + (col >> 2);
+            const int sh = (col & 3) * 8;
+            const uint32_t* crow = (const uint32_t*)(s_cur + mbl * 16);
+            uint32_t diff = 0;
+            for (int j = 0; j < 16 && diff == 0; j++) {   // early out on the first differing row
+                const uint32_t w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3], w4 = wrow[4];
+                diff |= __funnelshift_r(w0, w1, sh) ^ crow[0];
+                diff |= __funnelshift_r(w1, w2, sh) ^ crow[1];
+                diff |= __funnelshift_r(w2, w3, sh) ^ crow[2];
+                diff |= __funnelshift_r(w3, w4, sh) ^ crow[3];
+                wrow += L.pitch_w;
+                crow += L.seg_mbs * 4;
             }
-            if (lane == 0) p.mezero[((size_t)gop * g.nmb + mby * g.mbw + mbx) * 8 + state] = z;
+            z |= (unsigned long long)__ballot_sync(0xffffffffu, diff == 0) << (32 * h2);
         }
+        if (lane == 0) p.mezero[((size_t)gop * g.nmb + mby * g.mbw + m0 + mbl) * 8 + state] = z;
     }
 }
 

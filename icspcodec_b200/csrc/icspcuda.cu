@@ -56,6 +56,7 @@ struct icsp_ctx {
     cudaEvent_t slots[8] = {};
     char err[256] = "";
     size_t me_smem = 0, intra_smem = 0, chain_smem = 0;
+    MeLayout me{};
 };
 
 namespace {
@@ -127,6 +128,26 @@ int upload_tables(icsp_ctx* c)
     CU(cudaMemcpyToSymbol(c_IZ, IZ, sizeof(IZ)));
     CU(cudaMemcpyToSymbol(c_cand, cand, sizeof(cand)));
     CU(cudaMemcpyToSymbol(c_next, next, sizeof(next)));
+    // (round, lane) slots of the ME kernel: candidate -> shared-memory bank residue of its first word, for a row pitch
+    // == 8 (mod 32) words and copy offsets {0,1,1,1} (see me_sad_kernel).  Two candidates per residue -> one per round.
+    unsigned char slot[8][2][32];
+    for (int s = 0; s < 8; s++) {
+        int sl[2][32];
+        for (auto& r : sl) for (int& v : r) v = -1;
+        std::vector<int> left;
+        for (int idx = 0; idx < 64; idx++) {
+            const int dx = cand[s][idx][0], dy = cand[s][idx][1];
+            const int res = ((((16 + dx) & 3) ? 1 : 0) + (16 + dy) * 8 + ((16 + dx) >> 2)) & 31;
+            if (sl[0][res] < 0) sl[0][res] = idx;
+            else if (sl[1][res] < 0) sl[1][res] = idx;
+            else left.push_back(idx);
+        }
+        for (int idx : left)
+            for (int q = 0; q < 64; q++)
+                if (sl[q >> 5][q & 31] < 0) { sl[q >> 5][q & 31] = idx; break; }
+        for (int r = 0; r < 2; r++) for (int l = 0; l < 32; l++) slot[s][r][l] = (unsigned char)sl[r][l];
+    }
+    CU(cudaMemcpyToSymbol(c_slot, slot, sizeof(slot)));
     return ICSP_OK;
 }
 
@@ -186,7 +207,17 @@ int check_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
     return ICSP_OK;
 }
 
-int me_threads(const Geom& g) { return g.mbw * 32 > 1024 ? 1024 : g.mbw * 32; }
+MeLayout me_layout(const Geom& g)
+{
+    MeLayout L;
+    L.nseg = (g.mbw + 21) / 22;
+    L.seg_mbs = (g.mbw + L.nseg - 1) / L.nseg;
+    L.row_w = (L.seg_mbs * 16 + 32) / 4;
+    L.pitch_w = L.row_w + 1;
+    while ((L.pitch_w & 31) != 8) L.pitch_w++;
+    L.copy_w = 48 * L.pitch_w;
+    return L;
+}
 
 // motion estimation of step t for every GOP: speculative state-0 search, then the exact carried-state fallback
 // (no-ops unless some search of the frame broke early)
@@ -195,11 +226,13 @@ int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G)
     const Geom& g = c->g;
     CU(cudaMemsetAsync(c->d_meflag, 0, sizeof(uint32_t) * G, c->stream));
     CU(cudaMemsetAsync(c->d_mestate, 0, (size_t)G * g.nmb, c->stream));
-    dim3 grid(g.mbh, G);
-    { LaunchScope ls(c, K_ME_SAD); me_sad_kernel<<<grid, me_threads(g), c->me_smem, c->stream>>>(g, p, st, 0); }
-    { LaunchScope ls(c, K_ME_ZERO); me_zero_kernel<<<grid, me_threads(g), c->me_smem, c->stream>>>(g, p, st); }
+    const MeLayout& L = c->me;
+    dim3 grid(g.mbh * L.nseg, G);
+    const int threads = L.seg_mbs * 32;
+    { LaunchScope ls(c, K_ME_SAD); me_sad_kernel<<<grid, threads, c->me_smem, c->stream>>>(g, L, p, st, 0); }
+    { LaunchScope ls(c, K_ME_ZERO); me_zero_kernel<<<grid, threads, c->me_smem, c->stream>>>(g, L, p, st); }
     { LaunchScope ls(c, K_ME_CHAIN); me_chain_kernel<<<G, 32, 0, c->stream>>>(g, p); }
-    { LaunchScope ls(c, K_ME_FIXUP); me_sad_kernel<<<grid, me_threads(g), c->me_smem, c->stream>>>(g, p, st, 1); }
+    { LaunchScope ls(c, K_ME_FIXUP); me_sad_kernel<<<grid, threads, c->me_smem, c->stream>>>(g, L, p, st, 1); }
     return ICSP_OK;
 }
 
@@ -256,18 +289,27 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     CUB(cudaMemsetAsync(c->d_minsad, 0, F * nmb * 4, c->stream));
     for (auto& s : c->slots) CUB(cudaEventCreate(&s));
     if (upload_tables(c) != ICSP_OK) return bail(ICSP_ERR_CUDA);
-    c->me_smem = (size_t)48 * (g.w + 32) + (size_t)16 * g.w + 32;
+    c->me = me_layout(g);
+    c->me_smem = me_smem_bytes(c->me);
     c->intra_smem = intra_smem_bytes(g);
     c->chain_smem = (size_t)6 * g.nmb * sizeof(int);
     if (c->me_smem > 200 * 1024 || c->intra_smem > 180 * 1024 || c->chain_smem > 200 * 1024) {
         fail(c, ICSP_ERR_PARAM, "frame %dx%d too large for the shared-memory staging of this build", width, height);
         return bail(ICSP_ERR_PARAM);
     }
-    CUB(cudaFuncSetAttribute(me_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->me_smem));
-    CUB(cudaFuncSetAttribute(me_zero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->me_smem));
-    CUB(cudaFuncSetAttribute(intra_luma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->intra_smem));
-    CUB(cudaFuncSetAttribute(intra_luma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->intra_smem));
-    CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->chain_smem));
+    {   // the attribute is per function (process wide), not per context: always opt in to the device maximum
+        int optin = 0;
+        CUB(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        if ((size_t)optin < c->me_smem || (size_t)optin < c->intra_smem + 20 * 1024 || (size_t)optin < c->chain_smem) {
+            fail(c, ICSP_ERR_PARAM, "frame %dx%d needs more shared memory than the device offers", width, height);
+            return bail(ICSP_ERR_PARAM);
+        }
+        CUB(cudaFuncSetAttribute(me_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(me_zero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(intra_luma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
+        CUB(cudaFuncSetAttribute(intra_luma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
+        CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    }
     CUB(cudaStreamSynchronize(c->stream));
 #undef CUB
     *out = c;
