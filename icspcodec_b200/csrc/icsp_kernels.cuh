@@ -445,7 +445,7 @@ struct MeLayout {
     int copy_w;    // words per copy = 48*pitch_w
 };
 __constant__ unsigned char c_slot[8][2][32];   // start state, round, lane -> visit index handled by that lane
-__host__ __device__ inline int me_copy_off(const MeLayout& L, int s) { return s * L.copy_w + (s ? 1 : 0); }
+__host__ __device__ inline int me_copy_off(const MeLayout& L, int s) { return s * L.copy_w + (s ? 1 : 0); }  // +1: see me_stage
 __host__ __device__ inline size_t me_smem_bytes(const MeLayout& L) { return (size_t)(4 * L.copy_w + 8) * 4 + (size_t)16 * L.seg_mbs * 16; }
 
 __device__ __forceinline__ uint4 window_chunk(const uint8_t* __restrict__ plane, int w, int h, int py, int pxc)
@@ -464,31 +464,40 @@ __device__ __forceinline__ uint4 window_chunk(const uint8_t* __restrict__ plane,
     return o;
 }
 
-// stage window (copy 0, and the shifted copies when SHIFTED) + current rows of segment (mby, seg)
+// Stage the window and the current rows of segment (mby, m0..m0+nmbs).  One warp per window row, one lane per
+// 16-byte chunk: copy 0 is the plain window; copy s (s = 1..3) holds the window shifted left by s bytes and stored
+// one word to the right (word i+1 of copy s = window bytes [4i+s, 4i+s+4)), so all four stores are aligned STS.128.
 template <bool SHIFTED>
 __device__ __forceinline__ void me_stage(const Geom& g, const MeLayout& L, uint32_t* s_win, uint8_t* s_cur,
                                          const uint8_t* __restrict__ cury, const uint8_t* __restrict__ refy, int mby, int m0, int nmbs)
 {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int chunks = nmbs + 2;
-    for (int i = threadIdx.x; i < 48 * chunks; i += blockDim.x) {
-        const int row = i / chunks, c = i - row * chunks;
-        *(uint4*)(s_win + row * L.pitch_w + c * 4) = window_chunk(refy, g.w, g.h, mby * 16 + row, m0 + c);
-    }
-    for (int i = threadIdx.x; i < 16 * nmbs; i += blockDim.x) {
-        const int row = i / nmbs, c = i - row * nmbs;
-        *(uint4*)(s_cur + (row * L.seg_mbs + c) * 16) = __ldg((const uint4*)(cury + (size_t)(mby * 16 + row) * g.w + (m0 + c) * 16));
-    }
-    __syncthreads();
-    if (SHIFTED) {
-        const int rw = chunks * 4;
-        for (int i = threadIdx.x; i < 48 * rw; i += blockDim.x) {
-            const int row = i / rw, c = i - row * rw;
-            const uint32_t a = s_win[row * L.pitch_w + c], b = (c + 1 < rw) ? s_win[row * L.pitch_w + c + 1] : 0u;
+    for (int row = warp; row < 48; row += nwarps) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (lane < chunks) v = window_chunk(refy, g.w, g.h, mby * 16 + row, m0 + lane);
+        uint32_t* dst = s_win + row * L.pitch_w + lane * 4;
+        if (lane < chunks) *(uint4*)dst = v;
+        if (SHIFTED) {
+            uint32_t prev = __shfl_up_sync(0xffffffffu, v.w, 1);
+            if (lane == 0) prev = 0;
+            if (lane < chunks) {
 #pragma unroll
-            for (int sft = 1; sft < 4; sft++) s_win[me_copy_off(L, sft) + row * L.pitch_w + c] = __funnelshift_r(a, b, 8 * sft);
+                for (int sft = 1; sft < 4; sft++) {
+                    uint4 o;
+                    o.x = __funnelshift_r(prev, v.x, 8 * sft);
+                    o.y = __funnelshift_r(v.x, v.y, 8 * sft);
+                    o.z = __funnelshift_r(v.y, v.z, 8 * sft);
+                    o.w = __funnelshift_r(v.z, v.w, 8 * sft);
+                    *(uint4*)(dst + sft * L.copy_w) = o;
+                }
+            }
         }
-        __syncthreads();
     }
+    for (int row = warp; row < 16; row += nwarps)
+        if (lane < nmbs)
+            *(uint4*)(s_cur + (row * L.seg_mbs + lane) * 16) = __ldg((const uint4*)(cury + (size_t)(mby * 16 + row) * g.w + (m0 + lane) * 16));
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fixup)

@@ -1,0 +1,191 @@
+#include "bitstream.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <stdexcept>
+#include <thread>
+
+namespace icsp_host {
+
+void BitString::flush_word()
+{
+    words_.push_back(acc_);
+    acc_ = 0;
+    accbits_ = 0;
+}
+
+void BitString::put(uint32_t value, int nbits)
+{
+    if (nbits <= 0) return;
+    const uint64_t v = (nbits == 32) ? value : (value & ((1u << nbits) - 1u));
+    const int room = 64 - accbits_;
+    if (nbits < room) {
+        acc_ = (acc_ << nbits) | v;
+        accbits_ += nbits;
+    } else {
+        const int rest = nbits - room;            // bits that do not fit
+        acc_ = (room == 64) ? (v >> rest) : ((acc_ << room) | (v >> rest));
+        flush_word();
+        if (rest) { acc_ = v & ((1ull << rest) - 1ull); accbits_ = rest; }
+    }
+    nbits_ += nbits;
+}
+
+void BitString::append(const BitString& o)
+{
+    for (uint64_t w : o.words_) { put((uint32_t)(w >> 32), 32); put((uint32_t)w, 32); }
+    if (o.accbits_ > 32) { put((uint32_t)(o.acc_ >> 32), o.accbits_ - 32); put((uint32_t)o.acc_, 32); }
+    else put((uint32_t)o.acc_, o.accbits_);
+}
+
+std::vector<uint8_t> BitString::reference_body() const
+{
+    std::vector<uint8_t> out;
+    out.reserve(nbits_ / 8 + 1);
+    for (uint64_t w : words_)
+        for (int b = 7; b >= 0; b--) out.push_back((uint8_t)(w >> (8 * b)));
+    int left = accbits_;
+    while (left >= 8) { out.push_back((uint8_t)(acc_ >> (left - 8))); left -= 8; }
+    out.push_back(left ? (uint8_t)(acc_ & ((1u << left) - 1u)) : (uint8_t)0);   // right-aligned tail / extra zero byte
+    return out;
+}
+
+void put_vlc(BitString& bs, int v)
+{
+    const unsigned s = v >= 0 ? 1u : 0u;
+    const unsigned a = (unsigned)std::abs(v);
+    if (a == 0) { bs.put(0, 2); return; }
+    if (a == 1) { bs.put(0x4u | s, 4); return; }          // 0 1 0 s
+    int e = 31 - __builtin_clz(a);
+    if (e > 11) e = 11;                                    // last category: a >= 2048, 11 low bits of a-2048
+    const unsigned c = (a - (1u << e)) & ((1u << e) - 1u);
+    if (e <= 4) bs.put((((unsigned)(e + 2) << 1) | s), 4);            // 011/100/101/110 then sign
+    else bs.put((((1u << (e - 2)) - 1u) << 2) | s, e);                // (e-2) ones, 0, sign
+    bs.put(c, e);
+}
+
+static inline void put_block(BitString& bs, const int16_t* zz, int acflag)
+{
+    put_vlc(bs, zz[0]);
+    bs.put((unsigned)acflag, 1);
+    if (acflag == 1) { bs.put(0, 32); bs.put(0, 31); }                 // 63 zero bits (ENC:5069-5073)
+    else for (int k = 1; k < 64; k++) put_vlc(bs, zz[k]);
+}
+
+void encode_frame(BitString& bs, const Syntax& s, int frame, int nmb, bool intra)
+{
+    for (int mb = 0; mb < nmb; mb++) {
+        const size_t m = (size_t)frame * nmb + mb;
+        if (!intra) {
+            bs.put(1, 1);                                              // mv mode flag (ENC:5151)
+            put_vlc(bs, s.mvd[m * 2]);
+            put_vlc(bs, s.mvd[m * 2 + 1]);
+        }
+        for (int k = 0; k < 6; k++) {
+            if (intra && k < 4) bs.put(((unsigned)s.mpm[m * 4 + k] << 1) | s.ipm[m * 4 + k], 2);
+            put_block(bs, s.levels + (m * 6 + k) * 64, s.acflag[m * 6 + k]);
+        }
+    }
+}
+
+std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_threads)
+{
+    const int nmb = (p.width / 16) * (p.height / 16);
+    std::vector<BitString> per_frame((size_t)p.nframes);
+    n_threads = std::max(1, std::min(n_threads, p.nframes));
+    auto work = [&](int tid) {
+        for (int n = tid; n < p.nframes; n += n_threads) {
+            const bool intra = p.intra_period == 0 || n % p.intra_period == 0;
+            encode_frame(per_frame[n], s, n, nmb, intra);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    BitString all;
+    for (auto& f : per_frame) all.append(f);
+
+    std::vector<uint8_t> out(14);
+    // header (ENC.h:201-212 packed, ENC:4901-4922): "\0ICSP", u16 height, u16 width, QP_DC, QP_AC, DPCMmode=0, outro
+    out[0] = 0; out[1] = 'I'; out[2] = 'C'; out[3] = 'S'; out[4] = 'P';
+    out[5] = (uint8_t)(p.height & 255); out[6] = (uint8_t)(p.height >> 8);
+    out[7] = (uint8_t)(p.width & 255);  out[8] = (uint8_t)(p.width >> 8);
+    out[9] = (uint8_t)p.qp_dc; out[10] = (uint8_t)p.qp_ac; out[11] = 0;
+    const unsigned outro = ((unsigned)p.intra_period & 63u) << 7;     // 6 bits of intraPeriod, then 7 zero bits
+    out[12] = (uint8_t)(outro & 255); out[13] = (uint8_t)(outro >> 8);
+    const std::vector<uint8_t> body = all.reference_body();
+    out.insert(out.end(), body.begin(), body.end());
+    return out;
+}
+
+// ---- reader ------------------------------------------------------------------------------------------
+namespace {
+struct BitReader {
+    const uint8_t* p; uint64_t nbits, pos = 0;
+    int peek(uint64_t off) const { const uint64_t q = pos + off; return q < nbits ? (p[q >> 3] >> (7 - (q & 7))) & 1 : 0; }
+    int get() { const int v = peek(0); pos++; return v; }
+    int vlc()
+    {   // DCientropy (DEC:407-608) and its AC/MV twins: 3-bit category prefix, then unary extension from category 6 up
+        const int b0 = peek(0), b1 = peek(1), b2 = peek(2);
+        if (!b0 && !b1) { pos += 2; return 0; }
+        if (!b0 && b1 && !b2) { const int s = peek(3); pos += 4; return s ? 1 : -1; }
+        int e, prefix;
+        if (!(b0 && b1 && b2)) { e = ((b0 << 2) | (b1 << 1) | b2) - 2; prefix = 3; }
+        else {
+            int ones = 3;
+            while (ones < 10 && peek(ones)) ones++;
+            if (ones >= 10) return 0;              // no category matches: the reference leaves len = 0, val = 0
+            e = ones + 2; prefix = ones + 1;
+        }
+        const int s = peek(prefix);
+        int t = 0;
+        for (int n = 0; n < e; n++) t = (t << 1) | peek(prefix + 1 + n);
+        pos += prefix + 1 + e;
+        const int v = (1 << e) + t;
+        return s ? v : -v;
+    }
+};
+}  // namespace
+
+ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes)
+{
+    if (file.size() < 14) throw std::runtime_error("bitstream shorter than its 14-byte header");
+    ParsedStream ps;
+    ps.p.height = file[5] | (file[6] << 8);
+    ps.p.width = file[7] | (file[8] << 8);
+    ps.p.qp_dc = file[9]; ps.p.qp_ac = file[10];
+    const unsigned outro = file[12] | (file[13] << 8);
+    ps.p.intra_period = (outro & 0x1F80) >> 7;                        // DEC:29
+    ps.p.nframes = nframes;
+    if (ps.p.width <= 0 || ps.p.height <= 0 || (ps.p.width & 15) || (ps.p.height & 15)) throw std::runtime_error("bad geometry in header");
+    if (ps.p.intra_period < 1) throw std::runtime_error("intraPeriod 0 in header: the reference decoder divides by zero (DEC:201); encode with --intraPeriod 1 for all-intra");
+    if (ps.p.qp_dc == 0 || ps.p.qp_ac == 0) throw std::runtime_error("QP 0 in header");
+    const int nmb = (ps.p.width / 16) * (ps.p.height / 16);
+    const size_t N = (size_t)nframes * nmb;
+    ps.levels.assign(N * 384, 0); ps.acflag.assign(N * 6, 0); ps.mpm.assign(N * 4, 0); ps.ipm.assign(N * 4, 0); ps.mvd.assign(N * 2, 0);
+    BitReader r{file.data() + 14, (uint64_t)(file.size() - 14) * 8};
+    for (int n = 0; n < nframes; n++) {
+        const bool intra = ps.p.intra_period == 1 || n % ps.p.intra_period == 0;   // DEC:98, DEC:201
+        for (int mb = 0; mb < nmb; mb++) {
+            const size_t m = (size_t)n * nmb + mb;
+            if (!intra) {
+                (void)r.get();                                          // MVmodeflag (DEC:301)
+                ps.mvd[m * 2] = (int16_t)r.vlc();
+                ps.mvd[m * 2 + 1] = (int16_t)r.vlc();
+            }
+            for (int k = 0; k < 6; k++) {
+                if (intra && k < 4) { ps.mpm[m * 4 + k] = (uint8_t)r.get(); ps.ipm[m * 4 + k] = (uint8_t)r.get(); }
+                int16_t* zz = &ps.levels[(m * 6 + k) * 64];
+                zz[0] = (int16_t)r.vlc();
+                const int f = r.get();
+                ps.acflag[m * 6 + k] = (uint8_t)f;
+                if (f == 1) r.pos += 63;
+                else for (int q = 1; q < 64; q++) zz[q] = (int16_t)r.vlc();
+            }
+        }
+    }
+    return ps;
+}
+
+}  // namespace icsp_host

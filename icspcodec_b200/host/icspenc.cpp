@@ -1,0 +1,179 @@
+// icspenc — drop-in encoder front end: the reference's CLI (encoder_main.cpp:4-24, ENC:84-176) and frame loop
+// (single_thread_encoding ENC:217-245 / the GOP job model of ICSP_thread.cpp:39-77) on the host, the per-frame
+// core (intraPrediction / interPrediction) on the GPU through libicspcuda, then the host bitstream writer.
+//
+//   icspenc -i <name_cif.yuv> -n <frames> [-q Q | --qpdc D --qpac A] [--intraPeriod P] [-w W -h H]
+//           [--EnMultiThread T] [--gpus G] [--no-recon] [--quiet]
+//
+// Outputs, like the reference: <prefix>_compCIF_<QDC>_<QAC>_<IP>.bin (prefix = input name up to the first '_',
+// encoder_main.cpp:10-17) and test_yuv.yuv (reconstruction, ENC:6376-6421).  Unlike the reference's
+// --EnMultiThread mode, the bitstream is always written and tail frames (n % intraPeriod) are encoded.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/icspcuda.h"
+#include "bitstream.h"
+
+namespace {
+struct Options {
+    std::string input;
+    int frames = 1;             // README.md:30 documents 1 (the reference leaves it uninitialised, ENC:84-91)
+    int qdc = 0, qac = 0, ip = 0, threads = 0, gpus = 1;
+    int width = 352, height = 288;  // encoder_main.cpp:20 hard-wires CIF; -w/-h are accepted here
+    bool recon = true, quiet = false;
+};
+
+void help()
+{
+    printf("usage: ./icspenc [option] [values]\n"
+           "-i : input yuv sequence (planar I420; the name must contain '_')\n"
+           "-w : width (default 352)\n-h : height (default 288; without a value: this help)\n"
+           "-n : the number of frames(default is 1)\n-q : QP of DC and AC (16, 8, or 1)\n"
+           "--qpdc : QP of DC\n--qpac : QP of AC\n--intraPeriod: period of intra frame(0: All intra)\n"
+           "--EnMultiThread: host threads for the entropy coder (0 = all cores)\n"
+           "--gpus: GPUs to shard the GOPs over (default 1)\n--no-recon: do not write test_yuv.yuv\n--help : help message\n");
+}
+
+bool is_number(const char* s) { return s && *s && strspn(s, "0123456789") == strlen(s); }
+
+int parse(int argc, char** argv, Options& o)
+{
+    if (argc < 2) { fprintf(stderr, "[ERROR] unenough parameters in parsing_command\n"); return -1; }
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&](int& dst) { if (i + 1 >= argc) return false; dst = atoi(argv[++i]); return true; };
+        if (a == "--help") { help(); exit(0); }
+        else if (a == "-h") { if (i + 1 < argc && is_number(argv[i + 1])) o.height = atoi(argv[++i]); else { help(); exit(0); } }
+        else if (a == "-w") { if (!val(o.width)) return -1; }
+        else if (a == "-i") { if (i + 1 >= argc) return -1; o.input = argv[++i]; }
+        else if (a == "-n") { if (!val(o.frames)) return -1; }
+        else if (a == "-q") { if (!val(o.qdc)) return -1; o.qac = o.qdc; }
+        else if (a == "--qpdc") { if (!val(o.qdc)) return -1; }
+        else if (a == "--qpac") { if (!val(o.qac)) return -1; }
+        else if (a == "--intraPeriod") { if (!val(o.ip)) return -1; }
+        else if (a == "--EnMultiThread") { if (!val(o.threads)) return -1; }
+        else if (a == "--gpus") { if (!val(o.gpus)) return -1; }
+        else if (a == "--no-recon") o.recon = false;
+        else if (a == "--quiet") o.quiet = true;
+        else if (a[0] == '-') { fprintf(stderr, "[ERROR] uncorrect parameters in parsing_command\n"); return -1; }
+    }
+    return 0;
+}
+
+struct Shard {          // one GPU's contiguous range of GOPs
+    int device = 0;
+    int first_frame = 0, n_gops = 0, gop_len = 0;
+    int rc = 0;
+    std::string err;
+};
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    Options o;
+    if (parse(argc, argv, o)) return 1;
+    if (o.input.empty() || o.frames <= 0 || o.qdc <= 0 || o.qac <= 0 || o.ip < 0 || o.ip > 63 || (o.width & 15) || (o.height & 15) ||
+        o.qdc > 255 || o.qac > 255) {
+        fprintf(stderr, "[ERROR] uncorrect parameters (need -i, -n > 0, QP in 1..255, intraPeriod in 0..63, width/height multiples of 16)\n");
+        return 1;
+    }
+    const size_t us = o.input.find('_');
+    if (us == std::string::npos) { fprintf(stderr, "[ERROR] input file name must contain '_' (encoder_main.cpp:13)\n"); return 1; }
+    const std::string slash_stripped = o.input.substr(0, us);
+    const int nmb = (o.width / 16) * (o.height / 16);
+    const size_t fb = (size_t)o.width * o.height * 3 / 2;
+    const int n = o.frames;
+
+    FILE* fi = fopen(o.input.c_str(), "rb");
+    if (!fi) { fprintf(stderr, "[ERROR] cannot open %s\n", o.input.c_str()); return 1; }
+    uint8_t* frames = (uint8_t*)icsp_host_alloc((size_t)n * fb);
+    if (!frames) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host, %zu bytes); is a CUDA device present? libicspcuda has no CPU fallback\n", (size_t)n * fb); return 1; }
+    if (fread(frames, fb, n, fi) != (size_t)n) { fprintf(stderr, "[ERROR] %s holds fewer than %d frames of %dx%d\n", o.input.c_str(), n, o.width, o.height); return 1; }
+    fclose(fi);
+
+    // SoA outputs (pinned)
+    const size_t N = (size_t)n * nmb;
+    int16_t* levels = (int16_t*)icsp_host_alloc(N * 384 * 2);
+    uint8_t* acflag = (uint8_t*)icsp_host_alloc(N * 6);
+    uint8_t* mpm = (uint8_t*)icsp_host_alloc(N * 4);
+    uint8_t* ipm = (uint8_t*)icsp_host_alloc(N * 4);
+    int16_t* mvd = (int16_t*)icsp_host_alloc(N * 4);
+    uint8_t* recon = o.recon ? (uint8_t*)icsp_host_alloc((size_t)n * fb) : nullptr;
+    if (!levels || !acflag || !mpm || !ipm || !mvd || (o.recon && !recon)) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host)\n"); return 1; }
+
+    const auto t0 = std::chrono::steady_clock::now();
+    // frame loop: I-frame iff n % intraPeriod == 0 (0 = all intra).  Closed GOPs are independent jobs
+    // (ICSP_thread.cpp:39-77): full GOPs are sharded contiguously over the GPUs, the tail GOP goes to the last one.
+    const int gop = o.ip == 0 ? 1 : o.ip;
+    const int full = n / gop, tail = n - full * gop;
+    const int G = std::max(1, o.gpus);
+    std::vector<Shard> shards;
+    for (int d = 0; d < G; d++) {
+        const int g0 = (int)((long long)full * d / G), g1 = (int)((long long)full * (d + 1) / G);
+        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, ""});
+    }
+    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, ""});
+    auto run_shard = [&](Shard& s) {
+        const int cnt = s.n_gops * s.gop_len;
+        const int per_call_gops = std::max(1, std::min(s.n_gops, 4096 / s.gop_len));   // bound device memory per call
+        icsp_ctx* ctx = nullptr;
+        s.rc = icsp_create(&ctx, s.device, o.width, o.height, per_call_gops * s.gop_len);
+        if (s.rc) { s.err = icsp_last_error(nullptr); return; }
+        for (int g = 0; g < s.n_gops && !s.rc; g += per_call_gops) {
+            const int ng = std::min(per_call_gops, s.n_gops - g);
+            const size_t f0 = (size_t)s.first_frame + (size_t)g * s.gop_len;
+            icsp_enc_out out{levels + f0 * nmb * 384, acflag + f0 * nmb * 6, mpm + f0 * nmb * 4, ipm + f0 * nmb * 4,
+                             mvd + f0 * nmb * 2, nullptr, nullptr, recon ? recon + f0 * fb : nullptr};
+            s.rc = icsp_encode_gops(ctx, frames + f0 * fb, ng, s.gop_len, o.qdc, o.qac, &out);
+            if (s.rc) s.err = icsp_last_error(ctx);
+        }
+        (void)cnt;
+        icsp_destroy(ctx);
+    };
+    {
+        // one host thread per GPU (shards of the same device run back to back on that thread)
+        std::vector<std::thread> th;
+        for (int d = 0; d < G; d++)
+            th.emplace_back([&, d] { for (auto& s : shards) if (s.device == d) run_shard(s); });
+        for (auto& t : th) t.join();
+    }
+    for (auto& s : shards)
+        if (s.rc) { fprintf(stderr, "[ERROR] GPU %d: %s (code %d)\n", s.device, s.err.c_str(), s.rc); return 1; }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (!o.quiet)
+        for (int f = 0; f < n; f++) printf("Encoding FRAME_%03d(%c) done!\n", f, (o.ip == 0 || f % o.ip == 0) ? 'I' : 'P');
+
+    icsp_host::StreamParams sp;
+    sp.width = o.width; sp.height = o.height; sp.qp_dc = o.qdc; sp.qp_ac = o.qac; sp.intra_period = o.ip; sp.nframes = n;
+    icsp_host::Syntax syn{levels, acflag, mpm, ipm, mvd};
+    const int hw = (int)std::thread::hardware_concurrency();
+    const std::vector<uint8_t> bin = icsp_host::write_stream(sp, syn, o.threads > 0 ? o.threads : std::max(1, hw));
+    const auto t2 = std::chrono::steady_clock::now();
+
+    char name[512];
+    snprintf(name, sizeof(name), "%s_compCIF_%d_%d_%d.bin", slash_stripped.c_str(), o.qdc, o.qac, o.ip);
+    FILE* fo = fopen(name, "wb");
+    if (!fo) { fprintf(stderr, "fail to open %s\n", name); return 1; }
+    fwrite(bin.data(), 1, bin.size(), fo);
+    fclose(fo);
+    if (o.recon) {
+        FILE* fr = fopen("test_yuv.yuv", "wb");
+        if (!fr) { fprintf(stderr, "fail to open test_yuv.yuv\n"); return 1; }
+        fwrite(recon, fb, n, fr);
+        fclose(fr);
+    }
+    if (!o.quiet) {
+        const double core = std::chrono::duration<double>(t1 - t0).count(), ent = std::chrono::duration<double>(t2 - t1).count();
+        fprintf(stderr, "icspenc: %d frames, GPU core %.3f s (%.0f fps), entropy+bitstream %.3f s, %zu bytes -> %s\n", n, core, n / core, ent,
+                bin.size(), name);
+    }
+    icsp_host_free(frames); icsp_host_free(levels); icsp_host_free(acflag); icsp_host_free(mpm); icsp_host_free(ipm);
+    icsp_host_free(mvd); icsp_host_free(recon);
+    return 0;
+}

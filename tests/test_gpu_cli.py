@@ -1,0 +1,86 @@
+"""GPU tests of the drop-in CLIs (icspcodec_b200/host/icspenc, icspdec): same options as the reference's
+encoder/decoder, outputs compared byte for byte with what the compiled reference produced (golden md5s), and —
+when oracle/_ref travelled to this box — with the reference binaries run live on the same input."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from icspcodec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = json.load(open(os.path.join(GOLD, "ref_cases.json")))
+ENC = os.path.join(ROOT, "icspcodec_b200", "host", "icspenc")
+DEC = os.path.join(ROOT, "icspcodec_b200", "host", "icspdec")
+
+
+def md5f(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    from icspcodec_b200 import build
+    build.build()
+    assert os.path.exists(ENC) and os.path.exists(DEC)
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[3], CASES[5], CASES[6], CASES[8]], ids=lambda c: f"{c['kind']}-q{c['qdc']}_{c['qac']}-ip{c['ip']}")
+def test_icspenc_icspdec_match_reference(tmp_path, case):
+    clip = synth.make_clip(case["kind"], case["nframes"], case["seed"])
+    clip.tofile(tmp_path / "clip_cif.yuv")
+    n, qdc, qac, ip = case["nframes"], case["qdc"], case["qac"], case["ip"]
+    subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", str(ip)],
+                   cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    binp = tmp_path / f"clip_compCIF_{qdc}_{qac}_{ip}.bin"
+    assert md5f(binp) == case["bin_md5"]                       # final bitstream, bit-exact vs the reference encoder
+    assert md5f(tmp_path / "test_yuv.yuv") == case["recon_md5"]  # reconstructed YUV
+    if ip > 0:
+        subprocess.run([DEC, str(n), binp.name, str(qdc), str(qac), str(ip), "clip_cif.yuv"], cwd=tmp_path, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out = "check_test_intra_yuv.yuv" if ip == 1 else "check_test_inter_yuv.yuv"
+        assert md5f(tmp_path / out) == case["dec_md5"]         # bit-exact YUV vs the reference decoder
+        assert (tmp_path / "experimental_Result_Decoding.txt").exists()
+
+
+def test_cli_options_and_tail_frames(tmp_path, oracle):
+    """-q, -w/-h, a frame count that is not a multiple of intraPeriod (the reference's MT mode drops the tail,
+    ICSP_thread.cpp:43; single-thread mode and this tool encode it), and --gpus 1."""
+    w, h, n = 176, 144, 7
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 200, size=(h + 8, w + 8)).astype(np.float64)
+    base = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1)) / 3
+    frames = []
+    for i in range(n):
+        y = np.clip(np.rint(base[i:i + h, i:i + w]), 0, 255).astype(np.uint8)
+        frames.append(np.concatenate([y.ravel(), np.full(w * h // 4, 120 + i, np.uint8), np.full(w * h // 4, 130 - i, np.uint8)]))
+    frames = np.stack(frames)
+    frames.tofile(tmp_path / "q_cif.yuv")
+    subprocess.run([ENC, "-i", "q_cif.yuv", "-n", str(n), "-q", "16", "--intraPeriod", "3", "-w", str(w), "-h", str(h), "--gpus", "1", "--quiet"],
+                   cwd=tmp_path, check=True)
+    s = oracle.encode(frames, w, h, 16, 16, 3)
+    assert open(tmp_path / "q_compCIF_16_16_3.bin", "rb").read() == oracle.write_bitstream(s, w, h, 16, 16, 3)
+    assert np.array_equal(np.fromfile(tmp_path / "test_yuv.yuv", np.uint8).reshape(n, -1), s.recon)
+    subprocess.run([DEC, str(n), "q_compCIF_16_16_3.bin", "16", "16", "3", "--out", "dec.yuv"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    ps, _ = oracle.parse_bitstream(open(tmp_path / "q_compCIF_16_16_3.bin", "rb").read(), n)
+    assert np.array_equal(np.fromfile(tmp_path / "dec.yuv", np.uint8).reshape(n, -1), oracle.decode(ps, w, h, 16, 16, 3))
+    # help / bad arguments never crash the process with a signal
+    assert subprocess.run([ENC, "--help"], capture_output=True).returncode == 0
+    assert subprocess.run([ENC, "-i", "q_cif.yuv", "-n", "2", "-q", "0"], cwd=tmp_path, capture_output=True).returncode == 1
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ICSPCodec_O2")), reason="oracle/_ref not on this box")
+def test_live_reference_binaries(tmp_path, oracle):
+    clip = synth.make_clip("highmotion", 8, 2025)
+    clip.tofile(tmp_path / "live_cif.yuv")
+    subprocess.run([ENC, "-i", "live_cif.yuv", "-n", "8", "-q", "8", "--intraPeriod", "4", "--quiet"], cwd=tmp_path, check=True)
+    rbin, rrec = oracle.ref_encode(clip, 8, 8, 4)
+    assert open(tmp_path / "live_compCIF_8_8_4.bin", "rb").read() == rbin
+    assert np.array_equal(np.fromfile(tmp_path / "test_yuv.yuv", np.uint8).reshape(8, -1), rrec)
+    subprocess.run([DEC, "8", "live_compCIF_8_8_4.bin", "8", "8", "4", "--out", "d.yuv"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    assert np.array_equal(np.fromfile(tmp_path / "d.yuv", np.uint8).reshape(8, -1), oracle.ref_decode(rbin, 8, 8, 8, 4))
