@@ -17,6 +17,7 @@ struct Geom {
     int cw, ch;    // chroma size
     int bw, bh;    // luma 8x8 grid
     int fb;        // bytes per I420 frame
+    unsigned magic_bw, magic_mbw;  // ceil(2^32/bw), ceil(2^32/mbw): n/d == umulhi(n, magic) while n*d < 2^32
 };
 
 // costable[u][x]: table 0 = encoder (binary32 literals widened, ENC.h:190-198), 1 = decoder (binary64, DEC.h:19-27)
@@ -26,6 +27,29 @@ __constant__ unsigned char c_ZZ[64];        // zig-zag position k -> raster inde
 __constant__ unsigned char c_IZ[64];        // raster index -> zig-zag position
 __constant__ signed char c_cand[8][64][2];  // spiral visiting order per carried start state: (dx,dy) (ENC:2101-2143)
 __constant__ unsigned char c_next[8][65];   // start state, moves made -> state handed to the next macroblock
+
+// compile-time copies of the zig-zag tables (indices are compile-time constants after full unrolling)
+__host__ __device__ constexpr int kZZ(int k)
+{
+    constexpr unsigned char t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return t[k];
+}
+__host__ __device__ constexpr int kIZ(int raster)
+{
+    for (int k = 0; k < 64; k++)
+        if (kZZ(k) == raster) return k;
+    return 0;
+}
+
+// x / q (C semantics, truncation toward zero), branch free: magic = ceil(2^31/q), result = umulhi(2|x|, magic).
+// Exact while |x|*q < 2^31; transform coefficients of 8-bit video are bounded by |x| <= 4080+4080 and q <= 255.
+__device__ __forceinline__ int div_magic(int x, unsigned magic)
+{
+    const unsigned r = __umulhi((unsigned)abs(x) << 1, magic);
+    return x < 0 ? -(int)r : (int)r;
+}
 
 __device__ __forceinline__ int med3(int a, int b, int c)
 {  // ENC:3677-3679
@@ -65,6 +89,27 @@ __device__ __forceinline__ void ref_row8(const uint8_t* __restrict__ P, int w, i
     }
 }
 
+// the same 8 pixels packed as two little-endian words (byte i of the pair = pixel x0+i)
+__device__ __forceinline__ uint2 ref_row8_packed(const uint8_t* __restrict__ P, int w, int h, int pad, int y, int x0)
+{
+    const int ux = x0 - pad, uy = y - pad;
+    if (uy >= 0 && uy < h && ux >= 0 && ux + 7 < w) {
+        const uint8_t* p = P + uy * w + ux;
+        const uintptr_t a = (uintptr_t)p;
+        const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = sh ? __ldg(q + 2) : 0u;
+        return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+    }
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        lo |= (uint32_t)ref_px(P, w, h, pad, y, x0 + i) << (8 * i);
+        hi |= (uint32_t)ref_px(P, w, h, pad, y, x0 + 4 + i) << (8 * i);
+    }
+    return make_uint2(lo, hi);
+}
+
 // ---- A.5 DC predictors on the 8x8 grid of one plane (dc = reconstructed DCs, row-major [bh][bw]) ----
 __device__ __forceinline__ int dc_pred_luma(const int* dc, int bw, int bx, int by)
 {  // ENC:3643-3990 reduced to geometry
@@ -92,6 +137,12 @@ __device__ __forceinline__ int quant(double D, int Q, bool chroma)
     const double x = __dadd_rn(D, 0.5);
     const int r = chroma ? __double2int_rd(x) : __double2int_rz(x);
     return r / Q;
+}
+__device__ __forceinline__ int quant_magic(double D, unsigned magic, bool chroma)
+{
+    const double x = __dadd_rn(D, 0.5);
+    const int r = chroma ? __double2int_rd(x) : __double2int_rz(x);
+    return div_magic(r, magic);
 }
 
 // ---- 8x8 transforms, one 8-lane group per block --------------------------------------------------

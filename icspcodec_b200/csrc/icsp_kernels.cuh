@@ -28,6 +28,7 @@ struct Step {
     int gop_len, t;  // f = g*gop_len + t
     int qdc, qac;
     int intra;       // 1: intra frame (transform kernels touch chroma only; luma is the wavefront kernel)
+    unsigned magic_ac, magic_dc;  // ceil(2^31/q), see div_magic
 };
 
 // item -> (mb, k, plane geometry)
@@ -43,7 +44,7 @@ __device__ __forceinline__ BlockId block_id(const Geom& g, int item, int intra)
     BlockId b;
     if (intra) { b.mb = item >> 1; b.k = 4 + (item & 1); }
     else { b.mb = item / 6; b.k = item - b.mb * 6; }
-    const int mbx = b.mb % g.mbw, mby = b.mb / g.mbw;
+    const int mby = (int)__umulhi((unsigned)b.mb, g.magic_mbw), mbx = b.mb - mby * g.mbw;
     if (b.k < 4) {
         b.plane = 0; b.bx = 2 * mbx + (b.k & 1); b.by = 2 * mby + (b.k >> 1);
         b.pw = g.w; b.ph = g.h; b.poff = 0; b.dcidx = b.by * g.bw + b.bx;
@@ -71,11 +72,25 @@ __device__ __forceinline__ void pred_row(const Geom& g, const BlockId& b, const 
         ref_row8(prevf + b.poff, g.cw, g.ch, 8, 8 + b.by * 8 + r - my / 2, 8 + b.bx * 8 - mx / 2, out);
 }
 
+__device__ __forceinline__ uint2 pred_row_packed(const Geom& g, const BlockId& b, const uint8_t* prevf, const int16_t* mvf, int r, int intra)
+{
+    if (intra) return make_uint2(0u, 0u);
+    const int mvw = *(const int*)(mvf + 2 * b.mb);
+    const int mx = (int)(int16_t)(mvw & 0xffff), my = mvw >> 16;
+    if (b.plane == 0) return ref_row8_packed(prevf, g.w, g.h, 16, 16 + b.by * 8 + r - my, 16 + b.bx * 8 - mx);
+    return ref_row8_packed(prevf + b.poff, g.cw, g.ch, 8, 8 + b.by * 8 + r - my / 2, 8 + b.bx * 8 - mx / 2);
+}
+
 // =====================================================================================================
 // Kernel A: residual + forward DCT + AC quantisation + zig-zag (R3, R5, R7, R8).  8 lanes per 8x8 block.
 // Writes AC levels (DC slot is filled by the DC chain kernel), ACflag and the scaled DC as a double.
 // =====================================================================================================
 constexpr int TR_THREADS = 128;  // 16 blocks per CTA
+// zig-zag positions needed by lane r of a block group, packed one byte per entry: g_izcol[r] byte v = IZ[v*8+r]
+// (column r, used after the forward transform), g_izrow[r] byte u = IZ[r*8+u] (row r, used before the inverse).
+// Global memory + read-only path: a lane-indexed __constant__ table would serialise 8 ways.
+__device__ uint2 g_izcol[8], g_izrow[8];
+__device__ __forceinline__ int iz_byte(const uint2& t, int i) { return (int)(((i < 4 ? t.x : t.y) >> (8 * (i & 3))) & 255u); }
 __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
@@ -90,14 +105,15 @@ __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtr
     const uint8_t* curf = p.cur + f * g.fb;
     const uint8_t* prevf = p.rec + (f - (st.intra ? 0 : 1)) * g.fb;
 
-    int e[8], pr[8];
+    int e[8];
+    const uint2 izc = __ldg(&g_izcol[r]);
     {
-        const uint2 cw = *(const uint2*)(curf + b.poff + (size_t)(b.by * 8 + r) * b.pw + b.bx * 8);
-        pred_row(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra, pr);
+        const uint2 cw = __ldg((const uint2*)(curf + b.poff + (size_t)(b.by * 8 + r) * b.pw + b.bx * 8));
+        const uint2 pr = pred_row_packed(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            e[i] = (int)((cw.x >> (8 * i)) & 255) - pr[i];
-            e[4 + i] = (int)((cw.y >> (8 * i)) & 255) - pr[4 + i];
+            e[i] = (int)((cw.x >> (8 * i)) & 255u) - (int)((pr.x >> (8 * i)) & 255u);
+            e[4 + i] = (int)((cw.y >> (8 * i)) & 255u) - (int)((pr.y >> (8 * i)) & 255u);
         }
     }
     double t[8], D[8];
@@ -109,8 +125,8 @@ __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtr
     int nz = 0;
 #pragma unroll
     for (int v = 0; v < 8; v++) {
-        const int L = quant(D[v], (v == 0 && r == 0) ? st.qdc : st.qac, chroma);
-        s_lv[grp][c_IZ[v * 8 + r]] = (int16_t)L;
+        const int L = quant_magic(D[v], st.magic_ac, chroma);   // the DC slot (v == 0, r == 0) is rewritten by the DC chain kernel
+        s_lv[grp][iz_byte(izc, v)] = (int16_t)L;
         if (!(v == 0 && r == 0)) nz |= L;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, nz != 0);
@@ -214,19 +230,13 @@ __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtr
     const uint8_t* prevf = p.rec + (f - (st.intra ? 0 : 1)) * g.fb;
 
     const int16_t* lv = p.levels + ((f * g.nmb + b.mb) * 6 + b.k) * 64;
-    *(uint4*)(&s_lv[grp][8 * r]) = *(const uint4*)(lv + 8 * r);
-    int pr[8];
-    pred_row(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra, pr);
-    {
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { lo |= (uint32_t)pr[i] << (8 * i); hi |= (uint32_t)pr[4 + i] << (8 * i); }
-        *(uint2*)(&s_px[grp][8 * r]) = make_uint2(lo, hi);
-    }
+    *(uint4*)(&s_lv[grp][8 * r]) = __ldg((const uint4*)(lv + 8 * r));
+    const uint2 izr = __ldg(&g_izrow[r]);
+    *(uint2*)(&s_px[grp][8 * r]) = pred_row_packed(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra);
     __syncwarp();
     int q[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][c_IZ[r * 8 + u]] * st.qac;   // IQuantization_block
+    for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][iz_byte(izr, u)] * st.qac;   // IQuantization_block
     if (r == 0) q[0] = p.dcrec[(size_t)gop * 6 * g.nmb + b.dcidx];                 // level*QstepDC + P
     double t[8], R[8];
     idct_row<TAB>(q, t);                  // row y=r
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(IW_THREADS) intra_luma_kernel(Geom g, FramePtr
     uint8_t* recy = p.rec + f * g.fb;
     const int bw = g.bw, bh = g.bh, w = g.w;
     const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
+    const uint2 izc = __ldg(&g_izcol[r]), izr = __ldg(&g_izrow[r]);
 
     for (int wv = 0; wv < nwaves; wv++) {
         const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
@@ -374,8 +385,8 @@ __global__ void __launch_bounds__(IW_THREADS) intra_luma_kernel(Geom g, FramePtr
                 int nz = 0, L[8];
 #pragma unroll
                 for (int v = 0; v < 8; v++) {
-                    L[v] = quant(D[v], (v == 0 && r == 0) ? st.qdc : st.qac, false);
-                    s_lv[grp][c_IZ[v * 8 + r]] = (int16_t)L[v];
+                    L[v] = quant_magic(D[v], (v == 0 && r == 0) ? st.magic_dc : st.magic_ac, false);
+                    s_lv[grp][iz_byte(izc, v)] = (int16_t)L[v];
                     if (!(v == 0 && r == 0)) nz |= L[v];
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, nz != 0);
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(IW_THREADS) intra_luma_kernel(Geom g, FramePtr
                 __syncwarp();
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][c_IZ[r * 8 + u]] * ((r == 0 && u == 0) ? st.qdc : st.qac);
+            for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][iz_byte(izr, u)] * ((r == 0 && u == 0) ? st.qdc : st.qac);
             if (r == 0) { q[0] += P; if (active) sm.dc[byy * bw + bx] = q[0]; }
             double t2[8], R[8];
             idct_row<TAB>(q, t2);
@@ -444,7 +455,10 @@ struct MeLayout {
     int pitch_w;   // words per window row in shared memory, == 8 (mod 32)
     int copy_w;    // words per copy = 48*pitch_w
 };
-__constant__ unsigned char c_slot[8][2][32];   // start state, round, lane -> visit index handled by that lane
+// start state, round, lane -> packed candidate handled by that lane: visit index | (dx & 255) << 8 | (dy & 255) << 16.
+// Lives in global memory (read through the read-only path, coalesced over lanes): a lane-indexed __constant__
+// table would serialise into 32 constant-cache replays per warp.
+__device__ uint32_t g_slot[8][2][32];
 __host__ __device__ inline int me_copy_off(const MeLayout& L, int s) { return s * L.copy_w + (s ? 1 : 0); }  // +1: see me_stage
 __host__ __device__ inline size_t me_smem_bytes(const MeLayout& L) { return (size_t)(4 * L.copy_w + 8) * 4 + (size_t)16 * L.seg_mbs * 16; }
 
@@ -526,8 +540,8 @@ __global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePt
     int vidx[2];
 #pragma unroll
     for (int rnd = 0; rnd < 2; rnd++) {
-        const int idx = c_slot[state][rnd][lane];
-        const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
+        const uint32_t pk = __ldg(&g_slot[state][rnd][lane]);
+        const int idx = pk & 255, dx = (int)(int8_t)(pk >> 8), dy = (int)(int8_t)(pk >> 16);
         const int col = mbl * 16 + 16 + dx;   // window byte column of the candidate's first pixel
         const uint32_t* wrow = s_win + me_copy_off(L, col & 3) + (16 + dy) * L.pitch_w + (col >> 2);
         const uint4* crow = (const uint4*)(s_cur + mbl * 16);
@@ -561,8 +575,8 @@ __global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePt
     if (lane == 0) {
         const int mb = mby * g.mbw + m0 + mbl;
         // mv = MB origin - best position (ENC:2145-2146)
-        p.mv[(f * g.nmb + mb) * 2] = (int16_t)(-c_cand[state][win][0]);
-        p.mv[(f * g.nmb + mb) * 2 + 1] = (int16_t)(-c_cand[state][win][1]);
+        const int wdx = c_cand[state][win][0], wdy = c_cand[state][win][1];   // warp-uniform index: broadcast
+        *(int*)(p.mv + (f * g.nmb + mb) * 2) = ((-wdx) & 0xffff) | ((-wdy) << 16);
         p.minsad[f * g.nmb + mb] = (int32_t)best;
         if (!fixup) {
             p.memoves[(size_t)gop * g.nmb + mb] = (uint8_t)moves;

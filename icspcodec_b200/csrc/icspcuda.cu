@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -81,6 +82,8 @@ int geom_init(Geom& g, int w, int h)
     if (w <= 0 || h <= 0 || (w & 15) || (h & 15)) return -1;
     g.w = w; g.h = h; g.mbw = w / 16; g.mbh = h / 16; g.nmb = g.mbw * g.mbh;
     g.cw = w / 2; g.ch = h / 2; g.bw = w / 8; g.bh = h / 8; g.fb = w * h * 3 / 2;
+    g.magic_bw = (unsigned)((0x100000000ull + g.bw - 1) / g.bw);
+    g.magic_mbw = (unsigned)((0x100000000ull + g.mbw - 1) / g.mbw);
     return 0;
 }
 
@@ -126,11 +129,24 @@ int upload_tables(icsp_ctx* c)
     CU(cudaMemcpyToSymbol(c_irt2, &irt2, sizeof(irt2)));
     CU(cudaMemcpyToSymbol(c_ZZ, ZZ, sizeof(ZZ)));
     CU(cudaMemcpyToSymbol(c_IZ, IZ, sizeof(IZ)));
+    {
+        uint2 izcol[8], izrow[8];
+        for (int r = 0; r < 8; r++) {
+            unsigned cl = 0, ch = 0, rl = 0, rh = 0;
+            for (int i = 0; i < 4; i++) {
+                cl |= (unsigned)IZ[i * 8 + r] << (8 * i); ch |= (unsigned)IZ[(4 + i) * 8 + r] << (8 * i);
+                rl |= (unsigned)IZ[r * 8 + i] << (8 * i); rh |= (unsigned)IZ[r * 8 + 4 + i] << (8 * i);
+            }
+            izcol[r] = make_uint2(cl, ch); izrow[r] = make_uint2(rl, rh);
+        }
+        CU(cudaMemcpyToSymbol(g_izcol, izcol, sizeof(izcol)));
+        CU(cudaMemcpyToSymbol(g_izrow, izrow, sizeof(izrow)));
+    }
     CU(cudaMemcpyToSymbol(c_cand, cand, sizeof(cand)));
     CU(cudaMemcpyToSymbol(c_next, next, sizeof(next)));
     // (round, lane) slots of the ME kernel: candidate -> shared-memory bank residue of its first word, for a row pitch
     // == 8 (mod 32) words and copy offsets {0,1,1,1} (see me_sad_kernel).  Two candidates per residue -> one per round.
-    unsigned char slot[8][2][32];
+    uint32_t slot[8][2][32];
     for (int s = 0; s < 8; s++) {
         int sl[2][32];
         for (auto& r : sl) for (int& v : r) v = -1;
@@ -145,9 +161,13 @@ int upload_tables(icsp_ctx* c)
         for (int idx : left)
             for (int q = 0; q < 64; q++)
                 if (sl[q >> 5][q & 31] < 0) { sl[q >> 5][q & 31] = idx; break; }
-        for (int r = 0; r < 2; r++) for (int l = 0; l < 32; l++) slot[s][r][l] = (unsigned char)sl[r][l];
+        for (int r = 0; r < 2; r++)
+            for (int l = 0; l < 32; l++) {
+                const int idx = sl[r][l];
+                slot[s][r][l] = (uint32_t)idx | ((uint32_t)(uint8_t)cand[s][idx][0] << 8) | ((uint32_t)(uint8_t)cand[s][idx][1] << 16);
+            }
     }
-    CU(cudaMemcpyToSymbol(c_slot, slot, sizeof(slot)));
+    CU(cudaMemcpyToSymbol(g_slot, slot, sizeof(slot)));
     return ICSP_OK;
 }
 
@@ -210,7 +230,9 @@ int check_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
 MeLayout me_layout(const Geom& g)
 {
     MeLayout L;
-    L.nseg = (g.mbw + 21) / 22;
+    int max_seg = 22;   // macroblocks per CTA; smaller segments = more resident CTAs per SM (staging overlaps compute)
+    if (const char* e = getenv("ICSP_ME_SEG")) { const int v = atoi(e); if (v >= 1 && v <= 22) max_seg = v; }
+    L.nseg = (g.mbw + max_seg - 1) / max_seg;
     L.seg_mbs = (g.mbw + L.nseg - 1) / L.nseg;
     L.row_w = (L.seg_mbs * 16 + 32) / 4;
     L.pitch_w = L.row_w + 1;
@@ -366,7 +388,7 @@ int icsp_enc_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
     const FramePtrs p = frame_ptrs(c);
     const int G = n_gops;
     for (int t = 0; t < gop_len; t++) {
-        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0};
+        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
         const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
         dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
         if (st.intra) {
@@ -445,7 +467,7 @@ int icsp_dec_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
     const FramePtrs p = frame_ptrs(c);
     const int G = n_gops;
     for (int t = 0; t < gop_len; t++) {
-        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0};
+        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
         const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
         dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
         if (st.intra) {
@@ -503,7 +525,7 @@ int icsp_me_sad(icsp_ctx* c, const uint8_t* cur_y, const uint8_t* ref_y, int n, 
     // pair i: reference luma -> rec frame 2i, current luma -> cur frame 2i+1 (gop_len 2, step 1)
     CU(cudaMemcpy2DAsync(c->d_rec, (size_t)2 * g.fb, ref_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpy2DAsync(c->d_cur + g.fb, (size_t)2 * g.fb, cur_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
-    Step st{2, 1, 1, 1, 0};
+    Step st{2, 1, 1, 1, 0, 0u, 0u};
     int rc = launch_me(c, frame_ptrs(c), st, n);
     if (rc) return rc;
     CU(cudaMemcpy2DAsync(mv, (size_t)g.nmb * 4, c->d_mv + (size_t)g.nmb * 2, (size_t)g.nmb * 8, (size_t)g.nmb * 4, n,
