@@ -3,6 +3,7 @@
 #include "../../include/icspcuda.h"
 #include "icsp_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -35,7 +36,14 @@ struct icsp_ctx {
     int device = 0;
     Geom g{};
     int cap = 0;  // frames
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // main stream: everything is ordered with respect to it
+    cudaStream_t cstream[4] = {};           // compute streams (GOP chunks round-robin: latency-bound kernels of one
+                                            // chunk overlap throughput-bound kernels of another)
+    cudaStream_t s_up = nullptr, s_down = nullptr;   // H2D / D2H copy streams of the pipelined one-shot calls
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
+    std::vector<cudaEvent_t> ev_chunk;      // per-chunk upload / compute-done events
+    int n_cstreams = 2;
+    int chunk_gops_target = 0;              // 0 = automatic
     // device SoA
     uint8_t *d_cur = nullptr, *d_rec = nullptr, *d_acflag = nullptr, *d_mpm = nullptr, *d_ipm = nullptr;
     int16_t *d_levels = nullptr, *d_mvd = nullptr, *d_mv = nullptr;
@@ -182,7 +190,7 @@ cudaEvent_t get_event(icsp_ctx* c)
 void fold_pending(icsp_ctx* c)
 {
     if (c->pending.empty()) return;
-    cudaStreamSynchronize(c->stream);
+    cudaDeviceSynchronize();
     for (auto& p : c->pending) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, p.a, p.b);
@@ -193,28 +201,32 @@ void fold_pending(icsp_ctx* c)
     c->pending.clear();
 }
 struct LaunchScope {
-    icsp_ctx* c; int k; cudaEvent_t a = nullptr, b = nullptr;
-    LaunchScope(icsp_ctx* c_, int k_) : c(c_), k(k_)
+    icsp_ctx* c; int k; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(icsp_ctx* c_, int k_, cudaStream_t s_ = nullptr) : c(c_), k(k_), s(s_ ? s_ : c_->stream)
     {
         c->launches++; c->count[k]++;
         if (c->profiling) {
-            if (c->pending.size() > 8192) fold_pending(c);
             a = get_event(c); b = get_event(c);
-            cudaEventRecord(a, c->stream);
+            cudaEventRecord(a, s);
         }
     }
     ~LaunchScope()
     {
-        if (c->profiling) { cudaEventRecord(b, c->stream); c->pending.push_back({k, a, b}); }
+        if (c->profiling) { cudaEventRecord(b, s); c->pending.push_back({k, a, b}); }
     }
 };
 
-FramePtrs frame_ptrs(icsp_ctx* c)
+// pointers of the chunk that starts at GOP g0 (frame g0*gop_len): kernels index GOPs from 0 inside a chunk
+FramePtrs frame_ptrs(icsp_ctx* c, int g0 = 0, int gop_len = 1)
 {
+    const size_t f0 = (size_t)g0 * gop_len, nmb = (size_t)c->g.nmb, G0 = (size_t)g0;
     FramePtrs p;
-    p.cur = c->d_cur; p.rec = c->d_rec; p.levels = c->d_levels; p.acflag = c->d_acflag; p.mpm = c->d_mpm; p.ipm = c->d_ipm;
-    p.mvd = c->d_mvd; p.mv = c->d_mv; p.minsad = c->d_minsad; p.dcraw = c->d_dcraw; p.dcrec = c->d_dcrec;
-    p.mestate = c->d_mestate; p.memoves = c->d_memoves; p.meflag = c->d_meflag; p.mezero = c->d_mezero;
+    p.cur = c->d_cur + f0 * c->g.fb; p.rec = c->d_rec + f0 * c->g.fb; p.levels = c->d_levels + f0 * nmb * 384;
+    p.acflag = c->d_acflag + f0 * nmb * 6; p.mpm = c->d_mpm + f0 * nmb * 4; p.ipm = c->d_ipm + f0 * nmb * 4;
+    p.mvd = c->d_mvd + f0 * nmb * 2; p.mv = c->d_mv + f0 * nmb * 2; p.minsad = c->d_minsad + f0 * nmb;
+    p.dcraw = c->d_dcraw + G0 * nmb * 6; p.dcrec = c->d_dcrec + G0 * nmb * 6;
+    p.mestate = c->d_mestate + G0 * nmb; p.memoves = c->d_memoves + G0 * nmb; p.meflag = c->d_meflag + G0;
+    p.mezero = c->d_mezero + G0 * nmb * 8;
     return p;
 }
 
@@ -243,18 +255,95 @@ MeLayout me_layout(const Geom& g)
 
 // motion estimation of step t for every GOP: speculative state-0 search, then the exact carried-state fallback
 // (no-ops unless some search of the frame broke early)
-int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G)
+int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream_t s)
 {
     const Geom& g = c->g;
-    CU(cudaMemsetAsync(c->d_meflag, 0, sizeof(uint32_t) * G, c->stream));
-    CU(cudaMemsetAsync(c->d_mestate, 0, (size_t)G * g.nmb, c->stream));
+    CU(cudaMemsetAsync(p.meflag, 0, sizeof(uint32_t) * G, s));
+    CU(cudaMemsetAsync(p.mestate, 0, (size_t)G * g.nmb, s));
     const MeLayout& L = c->me;
     dim3 grid(g.mbh * L.nseg, G);
     const int threads = L.seg_mbs * 32;
-    { LaunchScope ls(c, K_ME_SAD); me_sad_kernel<<<grid, threads, c->me_smem, c->stream>>>(g, L, p, st, 0); }
-    { LaunchScope ls(c, K_ME_ZERO); me_zero_kernel<<<grid, threads, c->me_smem, c->stream>>>(g, L, p, st); }
-    { LaunchScope ls(c, K_ME_CHAIN); me_chain_kernel<<<G, 32, 0, c->stream>>>(g, p); }
-    { LaunchScope ls(c, K_ME_FIXUP); me_sad_kernel<<<grid, threads, c->me_smem, c->stream>>>(g, L, p, st, 1); }
+    { LaunchScope ls(c, K_ME_SAD, s); me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0); }
+    { LaunchScope ls(c, K_ME_ZERO, s); me_zero_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st); }
+    { LaunchScope ls(c, K_ME_CHAIN, s); me_chain_kernel<<<G, 32, 0, s>>>(g, p); }
+    { LaunchScope ls(c, K_ME_FIXUP, s); me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 1); }
+    return ICSP_OK;
+}
+
+// every step of GOPs [g0, g0+G) on stream s
+int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+{
+    const Geom& g = c->g;
+    const FramePtrs p = frame_ptrs(c, g0, gop_len);
+    for (int t = 0; t < gop_len; t++) {
+        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
+        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
+        if (st.intra) {
+            LaunchScope ls(c, K_INTRA_ENC, s);
+            intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st);
+        } else {
+            const int rc = launch_me(c, p, st, G, s);
+            if (rc) return rc;
+        }
+        { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 0); }
+        { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0><<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
+    }
+    return ICSP_OK;
+}
+
+int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+{
+    const Geom& g = c->g;
+    const FramePtrs p = frame_ptrs(c, g0, gop_len);
+    for (int t = 0; t < gop_len; t++) {
+        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
+        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
+        if (st.intra) {
+            LaunchScope ls(c, K_INTRA_DEC, s);
+            intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st);
+        } else {
+            LaunchScope ls(c, K_MV_RECON, s);
+            mv_recon_kernel<<<G, 32, 0, s>>>(g, p, st);
+        }
+        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 1); }
+        { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1><<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
+    }
+    return ICSP_OK;
+}
+
+// GOPs per chunk: enough chunks to overlap (>= 2 per compute stream) but each big enough to fill the GPU
+int chunk_gops(const icsp_ctx* c, int n_gops, bool pipelined)
+{
+    if (c->chunk_gops_target > 0) return std::min(n_gops, c->chunk_gops_target);
+    const int min_chunk = 148;                       // one intra CTA per SM at least
+    // resident runs: few large chunks (launch overhead, tails); pipelined host calls: more chunks so that the
+    // first upload / last download are short (measured on B200: profiles/README.md)
+    int chunks = std::min(pipelined ? 8 : 4, std::max(1, n_gops / min_chunk));
+    return (n_gops + chunks - 1) / chunks;
+}
+
+cudaEvent_t chunk_event(icsp_ctx* c, size_t i)
+{
+    while (c->ev_chunk.size() <= i) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->ev_chunk.push_back(e); }
+    return c->ev_chunk[i];
+}
+
+// fork the compute streams off the main stream / join them back
+int fork_streams(icsp_ctx* c)
+{
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
+    return ICSP_OK;
+}
+int join_streams(icsp_ctx* c)
+{
+    for (int i = 0; i < c->n_cstreams; i++) {
+        CU(cudaEventRecord(c->ev_join[i], c->cstream[i]));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+    }
     return ICSP_OK;
 }
 
@@ -287,6 +376,13 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, ICSP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? ICSP_ERR_NOMEM : ICSP_ERR_CUDA); } } while (0)
     CUB(cudaSetDevice(device));
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("ICSP_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= 4) c->n_cstreams = v; }
+    if (const char* e = getenv("ICSP_CHUNK_GOPS")) { const int v = atoi(e); if (v >= 1) c->chunk_gops_target = v; }
+    for (int i = 0; i < 4; i++) CUB(cudaStreamCreateWithFlags(&c->cstream[i], cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 4; i++) CUB(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     const size_t F = (size_t)max_frames, nmb = (size_t)g.nmb;
     CUB(cudaMalloc(&c->d_cur, F * g.fb + 64));
     CUB(cudaMalloc(&c->d_rec, F * g.fb + 64));
@@ -342,7 +438,13 @@ void icsp_destroy(icsp_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaDeviceSynchronize();
+    for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
+    for (auto& st : c->cstream) if (st) cudaStreamDestroy(st);
+    if (c->s_up) cudaStreamDestroy(c->s_up);
+    if (c->s_down) cudaStreamDestroy(c->s_down);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& e : c->free_events) cudaEventDestroy(e);
     for (auto& s : c->slots) if (s) cudaEventDestroy(s);
@@ -384,24 +486,11 @@ int icsp_enc_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
     int rc = check_run(c, n_gops, gop_len, qdc, qac);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    const Geom& g = c->g;
-    const FramePtrs p = frame_ptrs(c);
-    const int G = n_gops;
-    for (int t = 0; t < gop_len; t++) {
-        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
-        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
-        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
-        if (st.intra) {
-            LaunchScope ls(c, K_INTRA_ENC);
-            intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, c->stream>>>(g, p, st);
-        } else {
-            rc = launch_me(c, p, st, G);
-            if (rc) return rc;
-        }
-        { LaunchScope ls(c, K_FDCT); fdct_quant_kernel<<<tgrid, TR_THREADS, 0, c->stream>>>(g, p, st); }
-        { LaunchScope ls(c, K_DCCHAIN); dc_chain_kernel<<<G, 128, c->chain_smem, c->stream>>>(g, p, st, 0); }
-        { LaunchScope ls(c, K_IDCT_ENC); idct_recon_kernel<0><<<tgrid, TR_THREADS, 0, c->stream>>>(g, p, st); }
-    }
+    const int cg = chunk_gops(c, n_gops, false);
+    if ((rc = fork_streams(c))) return rc;
+    for (int g0 = 0, i = 0; g0 < n_gops; g0 += cg, i++)
+        if ((rc = encode_chunk(c, g0, std::min(cg, n_gops - g0), gop_len, qdc, qac, c->cstream[i % c->n_cstreams]))) return rc;
+    if ((rc = join_streams(c))) return rc;
     CU(cudaGetLastError());
     return ICSP_OK;
 }
@@ -428,18 +517,50 @@ int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len
     int rc = check_run(c, n_gops, gop_len, qdc, qac);
     if (rc) return rc;
     if (!frames || !out) return fail(c, ICSP_ERR_PARAM, "icsp_encode_gops: NULL frames/out");
+    CU(cudaSetDevice(c->device));
+    const Geom& g = c->g;
+    const size_t nmb = (size_t)g.nmb;
     const int n = n_gops * gop_len;
-    if ((rc = icsp_enc_upload(c, frames, n))) return rc;
     // inter frames leave mpm/ipm untouched and intra frames leave mvd/mv/minsad untouched: clear them so the SoA
     // rows of the other frame type read as zero, as documented
-    const size_t N = (size_t)n, nmb = (size_t)c->g.nmb;
-    CU(cudaMemsetAsync(c->d_mpm, 0, N * nmb * 4, c->stream));
-    CU(cudaMemsetAsync(c->d_ipm, 0, N * nmb * 4, c->stream));
-    CU(cudaMemsetAsync(c->d_mvd, 0, N * nmb * 4, c->stream));
-    CU(cudaMemsetAsync(c->d_mv, 0, N * nmb * 4, c->stream));
-    CU(cudaMemsetAsync(c->d_minsad, 0, N * nmb * 4, c->stream));
-    if ((rc = icsp_enc_run(c, n_gops, gop_len, qdc, qac))) return rc;
-    if ((rc = icsp_enc_download(c, n, out))) return rc;
+    CU(cudaMemsetAsync(c->d_mpm, 0, (size_t)n * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_ipm, 0, (size_t)n * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_mvd, 0, (size_t)n * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_mv, 0, (size_t)n * nmb * 4, c->stream));
+    CU(cudaMemsetAsync(c->d_minsad, 0, (size_t)n * nmb * 4, c->stream));
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->s_up, c->ev_fork, 0));
+    for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
+    CU(cudaStreamWaitEvent(c->s_down, c->ev_fork, 0));
+    // software pipeline over GOP chunks: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three kinds of streams
+    const int cg = chunk_gops(c, n_gops, true);
+    for (int g0 = 0, i = 0; g0 < n_gops; g0 += cg, i++) {
+        const int G = std::min(cg, n_gops - g0);
+        const size_t f0 = (size_t)g0 * gop_len, cnt = (size_t)G * gop_len;
+        cudaStream_t cs = c->cstream[i % c->n_cstreams];
+        CU(cudaMemcpyAsync(c->d_cur + f0 * g.fb, frames + f0 * g.fb, cnt * g.fb, cudaMemcpyHostToDevice, c->s_up));
+        cudaEvent_t up = chunk_event(c, 2 * i), done = chunk_event(c, 2 * i + 1);
+        CU(cudaEventRecord(up, c->s_up));
+        CU(cudaStreamWaitEvent(cs, up, 0));
+        if ((rc = encode_chunk(c, g0, G, gop_len, qdc, qac, cs))) return rc;
+        CU(cudaEventRecord(done, cs));
+        CU(cudaStreamWaitEvent(c->s_down, done, 0));
+        cudaStream_t d = c->s_down;
+        if (out->levels) CU(cudaMemcpyAsync(out->levels + f0 * nmb * 384, c->d_levels + f0 * nmb * 384, cnt * nmb * 384 * 2, cudaMemcpyDeviceToHost, d));
+        if (out->acflag) CU(cudaMemcpyAsync(out->acflag + f0 * nmb * 6, c->d_acflag + f0 * nmb * 6, cnt * nmb * 6, cudaMemcpyDeviceToHost, d));
+        if (out->mpm) CU(cudaMemcpyAsync(out->mpm + f0 * nmb * 4, c->d_mpm + f0 * nmb * 4, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
+        if (out->ipm) CU(cudaMemcpyAsync(out->ipm + f0 * nmb * 4, c->d_ipm + f0 * nmb * 4, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
+        if (out->mvd) CU(cudaMemcpyAsync(out->mvd + f0 * nmb * 2, c->d_mvd + f0 * nmb * 2, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
+        if (out->mv) CU(cudaMemcpyAsync(out->mv + f0 * nmb * 2, c->d_mv + f0 * nmb * 2, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
+        if (out->minsad) CU(cudaMemcpyAsync(out->minsad + f0 * nmb, c->d_minsad + f0 * nmb, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
+        if (out->recon) CU(cudaMemcpyAsync(out->recon + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, d));
+    }
+    if ((rc = join_streams(c))) return rc;
+    CU(cudaEventRecord(c->ev_join[0], c->s_down));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+    CU(cudaEventRecord(c->ev_join[1], c->s_up));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+    CU(cudaGetLastError());
     return icsp_sync(c);
 }
 
@@ -463,23 +584,11 @@ int icsp_dec_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
     int rc = check_run(c, n_gops, gop_len, qdc, qac);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    const Geom& g = c->g;
-    const FramePtrs p = frame_ptrs(c);
-    const int G = n_gops;
-    for (int t = 0; t < gop_len; t++) {
-        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
-        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
-        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
-        if (st.intra) {
-            LaunchScope ls(c, K_INTRA_DEC);
-            intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, c->stream>>>(g, p, st);
-        } else {
-            LaunchScope ls(c, K_MV_RECON);
-            mv_recon_kernel<<<G, 32, 0, c->stream>>>(g, p, st);
-        }
-        { LaunchScope ls(c, K_DCCHAIN); dc_chain_kernel<<<G, 128, c->chain_smem, c->stream>>>(g, p, st, 1); }
-        { LaunchScope ls(c, K_IDCT_DEC); idct_recon_kernel<1><<<tgrid, TR_THREADS, 0, c->stream>>>(g, p, st); }
-    }
+    const int cg = chunk_gops(c, n_gops, false);
+    if ((rc = fork_streams(c))) return rc;
+    for (int g0 = 0, i = 0; g0 < n_gops; g0 += cg, i++)
+        if ((rc = decode_chunk(c, g0, std::min(cg, n_gops - g0), gop_len, qdc, qac, c->cstream[i % c->n_cstreams]))) return rc;
+    if ((rc = join_streams(c))) return rc;
     CU(cudaGetLastError());
     return ICSP_OK;
 }
@@ -526,7 +635,7 @@ int icsp_me_sad(icsp_ctx* c, const uint8_t* cur_y, const uint8_t* ref_y, int n, 
     CU(cudaMemcpy2DAsync(c->d_rec, (size_t)2 * g.fb, ref_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpy2DAsync(c->d_cur + g.fb, (size_t)2 * g.fb, cur_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
     Step st{2, 1, 1, 1, 0, 0u, 0u};
-    int rc = launch_me(c, frame_ptrs(c), st, n);
+    int rc = launch_me(c, frame_ptrs(c), st, n, c->stream);
     if (rc) return rc;
     CU(cudaMemcpy2DAsync(mv, (size_t)g.nmb * 4, c->d_mv + (size_t)g.nmb * 2, (size_t)g.nmb * 8, (size_t)g.nmb * 4, n,
                          cudaMemcpyDeviceToHost, c->stream));
