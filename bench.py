@@ -7,8 +7,9 @@ hot path over that whole batch (intra wavefront, ME/MC, DCT/quant, DC-DPCM, IDCT
 Multi-GPU: GOPs share no state, so every rank encodes its own 64 streams (weak scaling, no collective).
 
   value  frames/s, whole job, inputs already resident in HBM, timed with CUDA events on the library stream
-  e2e    frames/s through icsp_encode_gops() with pinned HOST buffers (H2D of the frames, kernels, D2H of every
-         syntax array + the reconstruction inside the timed region)
+  e2e    frames/s through icsp_encode_streams() with pinned HOST buffers: H2D of the frames, every kernel including
+         entropy coding + bit packing on the GPU, D2H of the finished bitstream bodies + the reconstruction, all inside
+         the timed region (`e2e_syntax` = the round-1 path icsp_encode_gops(): D2H of the int16 syntax arrays instead)
   roofline / kernels   per-kernel CUDA-event times measured live during the timed steps
   cpu_baseline         the compiled reference (oracle/_ref) --EnMultiThread on the host cores, bounded sample
 
@@ -221,6 +222,8 @@ ALG_BYTES = {  # algorithmic HBM bytes per frame each kernel must move (DESIGN.m
     "idct_recon_kernel<enc>": NMB * 6 * (128 + 4) + FB + FB,                 # levels, DC + ref -> recon
     "intra_luma_kernel<enc>": 2 * W * H + NMB * 4 * (128 + 3),               # cur Y -> recon Y, levels, flags
     "dc_chain_kernel": NMB * 6 * (8 + 4 + 2) + NMB * 8,
+    "entropy_size_kernel": NMB * 6 * (128 + 1 + 4),                          # levels + acflag -> block bit lengths
+    "entropy_pack_kernel": NMB * 6 * (128 + 1 + 4 + 4) + 20000,              # levels + offsets -> ~20 KB of bits per frame
 }
 
 
@@ -279,21 +282,45 @@ def ours(args) -> dict | None:
     stats = ctx.stats()
     ctx.set_profiling(False)
 
-    # ---- e2e: host buffers, H2D + kernels + D2H inside the timed region ---------------------------------------
-    ctx.encode_gops(pin_in.array, n_gops, 10, 8, 8, out=res, fields=e2e_fields)   # warm-up
+    # ---- value incl. GPU entropy coding (resident) -------------------------------------------------------------
+    ctx.entropy_run(args.streams, args.frames // 10, 10)
+    ctx.sync()
+    barrier()
+    ctx.event_record(2)
+    for _ in range(args.steps):
+        ctx.run(n_gops, 10, 8, 8)
+        ctx.entropy_run(args.streams, args.frames // 10, 10)
+    ctx.event_record(3)
+    ctx.sync()
+    barrier()
+    dev_en_ms = ctx.event_elapsed_ms(2, 3)
+
+    # ---- e2e: host buffers, H2D + kernels (+ GPU entropy coding) + D2H inside the timed region -----------------------
+    pin_bits = PinnedArray((n * (W * H + 32) + 64,), np.uint8)
+    _, sbits, _ = ctx.encode_streams(pin_in.array, args.streams, args.frames // 10, 10, 8, 8, True, pin_bits.array, res.recon)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.encode_streams(pin_in.array, args.streams, args.frames // 10, 10, 8, 8, True, pin_bits.array, res.recon)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = n * FB
+    body_bytes = int(sum((int(b) + 7) // 8 + 16 for b in sbits))
+    d2h = body_bytes + res.recon.nbytes
+    # round-1 path for comparison: syntax arrays over PCIe, entropy coding left to the host
+    ctx.encode_gops(pin_in.array, n_gops, 10, 8, 8, out=res, fields=e2e_fields)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         ctx.encode_gops(pin_in.array, n_gops, 10, 8, 8, out=res, fields=e2e_fields)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = n * FB
-    d2h = sum(getattr(res, f).nbytes for f in e2e_fields)
+    e2e_syn_s = time.perf_counter() - t0
+    d2h_syn = sum(getattr(res, f).nbytes for f in e2e_fields)
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, dev_en_ms, e2e_syn_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, dev_en_ms, e2e_syn_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -332,7 +359,13 @@ def ours(args) -> dict | None:
             "dtype": "f64+u8", "data": "synthetic (8 seeded high-motion clips per GPU, each reused 8x with a stream-specific circular shift)",
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps},
+                    "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
+                    "api": "icsp_encode_streams: frames in, finished bitstream bodies + reconstruction out (entropy coding on the GPU)",
+                    "bitstream_bytes_per_step": body_bytes},
+            "e2e_syntax": {"value": world * n * args.e2e_steps / (e2e_syn_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                           "d2h_bytes_per_step": int(d2h_syn), "ms_per_step": e2e_syn_ms / args.e2e_steps,
+                           "api": "icsp_encode_gops: int16 syntax arrays + reconstruction out, entropy coding left to the host"},
+            "value_with_entropy": world * n * args.steps / (dev_en_ms / 1e3),
             "roofline": roofline, "kernels": kernels,
             "me_sad_Gpos_per_s": kernels.get("me_sad_kernel", {}).get("Gpos_per_s")}
     if world == 1 and not args.no_cpu_baseline:

@@ -19,6 +19,11 @@ class DecIn(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("levels", "mpm", "ipm", "mvd")]
 
 
+class BitsOut(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("cap_bytes", C.c_size_t), ("stream_bits", C.c_void_p), ("stream_offset", C.c_void_p),
+                ("recon", C.c_void_p)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 40), ("launches", C.c_uint64), ("total_ms", C.c_double)]
 
@@ -32,6 +37,7 @@ EXPORTS = [
     "icsp_set_profiling", "icsp_reset_stats", "icsp_get_stats", "icsp_launch_count",
     "icsp_event_record", "icsp_event_elapsed_ms",
     "icsp_host_alloc", "icsp_host_free",
+    "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body",
 ]
 
 _lib = None
@@ -71,6 +77,11 @@ def load() -> C.CDLL:
     lib.icsp_launch_count.restype = C.c_uint64
     lib.icsp_event_record.argtypes = [vp, i]
     lib.icsp_event_elapsed_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
+    lib.icsp_encode_streams.argtypes = [vp, vp, i, i, i, i, i, C.POINTER(BitsOut)]
+    lib.icsp_entropy_run.argtypes = [vp, i, i, i]
+    lib.icsp_bits_download.argtypes = [vp, i, C.POINTER(BitsOut)]
+    lib.icsp_finish_body.argtypes = [vp, C.c_uint64]
+    lib.icsp_finish_body.restype = C.c_size_t
     lib.icsp_host_alloc.argtypes = [C.c_size_t]
     lib.icsp_host_alloc.restype = vp
     lib.icsp_host_free.argtypes = [vp]

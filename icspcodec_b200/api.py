@@ -55,6 +55,12 @@ class PinnedArray:
             pass
 
 
+def stream_header(w: int, h: int, qp_dc: int, qp_ac: int, intra_period: int) -> bytes:
+    """14-byte packed header (ENC.h:201-212, ENC:4901-4922)."""
+    outro = (intra_period & 63) << 7
+    return bytes([0, 73, 67, 83, 80, h & 255, h >> 8, w & 255, w >> 8, qp_dc & 255, qp_ac & 255, 0, outro & 255, outro >> 8])
+
+
 class IcspCuda:
     """One context = one GPU + one stream + device SoA buffers for up to `max_frames` frames."""
 
@@ -153,6 +159,57 @@ class IcspCuda:
 
     def sync(self):
         self._chk(self.lib.icsp_sync(self.h_ctx), "icsp_sync")
+
+    # ---- encoder with GPU entropy coding ------------------------------------------------
+    def encode_streams(self, frames: np.ndarray, n_streams: int, gops_per_stream: int, gop_len: int, qp_dc: int, qp_ac: int,
+                       want_recon: bool = False, bits_buf: np.ndarray | None = None, recon_buf: np.ndarray | None = None):
+        """Returns (bodies, stream_bits, recon): bodies[s] = MSB-first body bytes of stream s (ceil(bits/8) bytes)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = n_streams * gops_per_stream * gop_len
+        if frames.size != n * self.fb:
+            raise IcspError(f"expected {n} frames of {self.fb} bytes")
+        cap = n * (self.w * self.h + 32) + 64
+        bits = bits_buf if bits_buf is not None else np.zeros(cap, np.uint8)
+        sbits = np.zeros(n_streams, np.uint64)
+        soff = np.zeros(n_streams, np.uint64)
+        recon = (recon_buf if recon_buf is not None else np.zeros((n, self.fb), np.uint8)) if want_recon else None
+        o = _lib.BitsOut(_ptr(bits), bits.size, _ptr(sbits), _ptr(soff), _ptr(recon))
+        self._chk(self.lib.icsp_encode_streams(self.h_ctx, _ptr(frames), n_streams, gops_per_stream, gop_len, qp_dc, qp_ac, C.byref(o)),
+                  "icsp_encode_streams")
+        bodies = [bits[int(soff[s]): int(soff[s]) + (int(sbits[s]) + 7) // 8] for s in range(n_streams)]
+        return bodies, sbits, recon
+
+    def entropy_run(self, n_streams: int, gops_per_stream: int, gop_len: int):
+        self._chk(self.lib.icsp_entropy_run(self.h_ctx, n_streams, gops_per_stream, gop_len), "icsp_entropy_run")
+
+    def bits_download(self, n_streams: int, cap: int):
+        bits = np.zeros(cap, np.uint8)
+        sbits = np.zeros(n_streams, np.uint64)
+        soff = np.zeros(n_streams, np.uint64)
+        o = _lib.BitsOut(_ptr(bits), bits.size, _ptr(sbits), _ptr(soff), None)
+        self._chk(self.lib.icsp_bits_download(self.h_ctx, n_streams, C.byref(o)), "icsp_bits_download")
+        return [bits[int(soff[s]): int(soff[s]) + (int(sbits[s]) + 7) // 8] for s in range(n_streams)], sbits
+
+    def encode_sequence_bitstream(self, frames: np.ndarray, qp_dc: int, qp_ac: int, intra_period: int, want_recon: bool = False):
+        """One stream -> the complete reference-format file (header + body), entropy coded on the GPU.  Full GOPs and
+        the tail GOP are two device calls whose bit strings are concatenated here."""
+        frames = np.ascontiguousarray(frames, np.uint8).reshape(-1, self.fb)
+        n = frames.shape[0]
+        ip = 1 if intra_period == 0 else intra_period
+        full, tail = divmod(n, ip)
+        segs, recs = [], []
+        if full:
+            b, sb, r = self.encode_streams(frames[: full * ip], 1, full, ip, qp_dc, qp_ac, want_recon)
+            segs.append((b[0], int(sb[0]))); recs.append(r)
+        if tail:
+            b, sb, r = self.encode_streams(frames[full * ip:], 1, 1, tail, qp_dc, qp_ac, want_recon)
+            segs.append((b[0], int(sb[0]))); recs.append(r)
+        bits = np.concatenate([np.unpackbits(b)[:nb] for b, nb in segs])
+        nb = bits.size
+        body = bytearray(np.packbits(bits).tobytes()) if nb % 8 else bytearray(np.packbits(bits).tobytes() + b"\x00")
+        if nb % 8:
+            body[-1] = body[-1] >> (8 - nb % 8)              # reference tail rule (ENC:4895): right-aligned last byte
+        return stream_header(self.w, self.h, qp_dc, qp_ac, intra_period) + bytes(body), (np.concatenate(recs) if want_recon else None)
 
     # ---- decoder -----------------------------------------------------------------------------------
     def decode_gops(self, levels, mpm, ipm, mvd, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int) -> np.ndarray:

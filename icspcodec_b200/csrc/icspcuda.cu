@@ -2,6 +2,7 @@
 // Host side only orchestrates: one context = one GPU, one stream, SoA device buffers sized for max_frames.
 #include "../../include/icspcuda.h"
 #include "icsp_kernels.cuh"
+#include "icsp_entropy.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -21,12 +22,13 @@ thread_local char g_create_error[256] = "";
 
 enum KernelId {
     K_INTRA_ENC = 0, K_INTRA_DEC, K_FDCT, K_DCCHAIN, K_IDCT_ENC, K_IDCT_DEC, K_ME_SAD, K_ME_ZERO, K_ME_CHAIN, K_ME_FIXUP,
-    K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_COUNT
+    K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_EN_SIZE, K_EN_FSCAN, K_EN_SSCAN, K_EN_ZERO, K_EN_PACK, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "intra_luma_kernel<enc>", "intra_luma_kernel<dec>", "fdct_quant_kernel", "dc_chain_kernel", "idct_recon_kernel<enc>",
     "idct_recon_kernel<dec>", "me_sad_kernel", "me_zero_kernel", "me_chain_kernel", "me_sad_kernel(fixup)",
-    "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel"};
+    "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel", "entropy_size_kernel", "entropy_frame_scan_kernel",
+    "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel"};
 
 struct Pending { int k; cudaEvent_t a, b; };
 
@@ -55,6 +57,14 @@ struct icsp_ctx {
     unsigned long long* d_mezero = nullptr;
     void* d_shim = nullptr;
     size_t shim_bytes = 0;
+    // entropy coder (allocated on first use)
+    uint32_t* d_blkbits = nullptr;
+    unsigned long long *d_framebits = nullptr, *d_streambits = nullptr, *d_streamoff = nullptr, *d_chunktotal = nullptr;
+    uint32_t* d_overflow = nullptr;
+    uint8_t* d_bits = nullptr;
+    unsigned long long* h_tables = nullptr;   // pinned: [cap] stream bits, [cap] stream offsets, [64] chunk totals, [64] overflow
+    struct EnChunk { int s0, ns; size_t f0, nf; unsigned long long region_off, region_cap; };
+    std::vector<EnChunk> en_chunks;
     // instrumentation
     bool profiling = false;
     uint64_t launches = 0;
@@ -314,6 +324,53 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     return ICSP_OK;
 }
 
+// ---- entropy coding ------------------------------------------------------------------------------------
+constexpr int MAX_EN_CHUNKS = 64;
+int entropy_alloc(icsp_ctx* c)
+{
+    if (c->d_bits) return ICSP_OK;
+    const size_t F = (size_t)c->cap, nmb = (size_t)c->g.nmb;
+    CU(cudaMalloc(&c->d_blkbits, F * nmb * 6 * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_framebits, F * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_streambits, F * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_streamoff, F * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_chunktotal, MAX_EN_CHUNKS * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_overflow, MAX_EN_CHUNKS * sizeof(uint32_t)));
+    // same bound as the reference's own buffer: width*height bytes per frame (ENC:4874-4875), + alignment slack
+    CU(cudaMalloc(&c->d_bits, F * (size_t)c->g.w * c->g.h + F * 32 + 64));
+    CU(cudaHostAlloc(&c->h_tables, (2 * F + 2 * MAX_EN_CHUNKS) * sizeof(unsigned long long), cudaHostAllocDefault));
+    return ICSP_OK;
+}
+
+// entropy-code streams [s0, s0+ns) (frames [f0, f0+nf)) of the resident batch on stream s; chunk index ci
+int entropy_chunk(icsp_ctx* c, int ci, int s0, int ns, int gops_per_stream, int gop_len, cudaStream_t s)
+{
+    const Geom& g = c->g;
+    const int fps = gops_per_stream * gop_len;
+    const size_t f0 = (size_t)s0 * fps, nf = (size_t)ns * fps, nmb = (size_t)g.nmb;
+    const unsigned long long per_frame = (unsigned long long)g.w * g.h + 32;
+    icsp_ctx::EnChunk ch{s0, ns, f0, nf, f0 * per_frame, nf * per_frame};
+    if ((int)c->en_chunks.size() <= ci) c->en_chunks.resize(ci + 1);
+    c->en_chunks[ci] = ch;
+    FramePtrs p = frame_ptrs(c, (int)(f0 / gop_len), gop_len);
+    EntropyPtrs e;
+    e.blkbits = c->d_blkbits + f0 * nmb * 6; e.framebits = c->d_framebits + f0; e.streambits = c->d_streambits + s0;
+    e.streamoff = c->d_streamoff + s0; e.total = c->d_chunktotal + ci; e.overflow = c->d_overflow + ci;
+    e.bits = c->d_bits + ch.region_off; e.cap_bytes = ch.region_cap;
+    CU(cudaMemsetAsync(e.overflow, 0, sizeof(uint32_t), s));
+    dim3 grid((g.nmb * 6 + EN_THREADS - 1) / EN_THREADS, (unsigned)nf);
+    { LaunchScope ls(c, K_EN_SIZE, s); entropy_size_kernel<<<grid, EN_THREADS, 0, s>>>(g, p, e, gop_len); }
+    { LaunchScope ls(c, K_EN_FSCAN, s); entropy_frame_scan_kernel<<<(unsigned)nf, 256, 0, s>>>(g, e); }
+    {
+        LaunchScope ls(c, K_EN_SSCAN, s);
+        entropy_stream_scan_kernel<<<ns, 32, 0, s>>>(e, fps);
+        entropy_stream_offsets_kernel<<<1, 32, 0, s>>>(e, ns);
+    }
+    { LaunchScope ls(c, K_EN_ZERO, s); entropy_zero_kernel<<<296, 256, 0, s>>>(e); }
+    { LaunchScope ls(c, K_EN_PACK, s); entropy_pack_kernel<<<grid, EN_THREADS, 0, s>>>(g, p, e, gop_len, fps); }
+    return ICSP_OK;
+}
+
 // GOPs per chunk: enough chunks to overlap (>= 2 per compute stream) but each big enough to fill the GPU
 int chunk_gops(const icsp_ctx* c, int n_gops, bool pipelined)
 {
@@ -449,7 +506,9 @@ void icsp_destroy(icsp_ctx* c)
     for (auto& e : c->free_events) cudaEventDestroy(e);
     for (auto& s : c->slots) if (s) cudaEventDestroy(s);
     void* bufs[] = {c->d_cur, c->d_rec, c->d_levels, c->d_acflag, c->d_mpm, c->d_ipm, c->d_mvd, c->d_mv, c->d_minsad, c->d_dcraw,
-                    c->d_dcrec, c->d_mestate, c->d_memoves, c->d_meflag, c->d_mezero, c->d_shim};
+                    c->d_dcrec, c->d_mestate, c->d_memoves, c->d_meflag, c->d_mezero, c->d_shim, c->d_blkbits, c->d_framebits,
+                    c->d_streambits, c->d_streamoff, c->d_chunktotal, c->d_overflow, c->d_bits};
+    if (c->h_tables) cudaFreeHost(c->h_tables);
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -554,6 +613,146 @@ int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len
         if (out->mv) CU(cudaMemcpyAsync(out->mv + f0 * nmb * 2, c->d_mv + f0 * nmb * 2, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
         if (out->minsad) CU(cudaMemcpyAsync(out->minsad + f0 * nmb, c->d_minsad + f0 * nmb, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
         if (out->recon) CU(cudaMemcpyAsync(out->recon + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, d));
+    }
+    if ((rc = join_streams(c))) return rc;
+    CU(cudaEventRecord(c->ev_join[0], c->s_down));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+    CU(cudaEventRecord(c->ev_join[1], c->s_up));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+    CU(cudaGetLastError());
+    return icsp_sync(c);
+}
+
+// ---- encoder + GPU entropy coding ------------------------------------------------------------------------
+size_t icsp_finish_body(uint8_t* body, uint64_t nbits)
+{
+    const size_t full = (size_t)(nbits / 8);
+    const int tail = (int)(nbits % 8);
+    body[full] = tail ? (uint8_t)(body[full] >> (8 - tail)) : (uint8_t)0;   // right-align the tail (ENC:4895 writes bits/8+1 bytes)
+    return full + 1;
+}
+
+static int check_streams(icsp_ctx* c, int n_streams, int gops_per_stream, int gop_len)
+{
+    if (!c) return ICSP_ERR_PARAM;
+    if (n_streams <= 0 || gops_per_stream <= 0 || gop_len <= 0) return fail(c, ICSP_ERR_PARAM, "bad stream geometry");
+    if ((long long)n_streams * gops_per_stream * gop_len > c->cap) return fail(c, ICSP_ERR_CAPACITY, "more frames than capacity %d", c->cap);
+    if ((long long)n_streams * gops_per_stream > 65535) return fail(c, ICSP_ERR_PARAM, "more than 65535 GOPs per call");
+    return ICSP_OK;
+}
+
+// streams per chunk for the entropy path (chunks are whole streams)
+static int chunk_streams(const icsp_ctx* c, int n_streams, int gops_per_stream, bool pipelined)
+{
+    const int cg = chunk_gops(c, n_streams * gops_per_stream, pipelined);
+    int cs = std::max(1, cg / gops_per_stream);
+    while ((n_streams + cs - 1) / cs > MAX_EN_CHUNKS) cs++;
+    return cs;
+}
+
+int icsp_entropy_run(icsp_ctx* c, int n_streams, int gops_per_stream, int gop_len)
+{
+    int rc = check_streams(c, n_streams, gops_per_stream, gop_len);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if ((rc = entropy_alloc(c))) return rc;
+    const int cs = chunk_streams(c, n_streams, gops_per_stream, false);
+    c->en_chunks.clear();
+    if ((rc = fork_streams(c))) return rc;
+    for (int s0 = 0, i = 0; s0 < n_streams; s0 += cs, i++)
+        if ((rc = entropy_chunk(c, i, s0, std::min(cs, n_streams - s0), gops_per_stream, gop_len, c->cstream[i % c->n_cstreams]))) return rc;
+    if ((rc = join_streams(c))) return rc;
+    CU(cudaGetLastError());
+    return ICSP_OK;
+}
+
+// copy the tables of chunk ci to the pinned staging area (async on stream s)
+static int tables_to_host(icsp_ctx* c, int ci, cudaStream_t s)
+{
+    const auto& ch = c->en_chunks[ci];
+    const size_t F = (size_t)c->cap;
+    CU(cudaMemcpyAsync(c->h_tables + ch.s0, c->d_streambits + ch.s0, ch.ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(c->h_tables + F + ch.s0, c->d_streamoff + ch.s0, ch.ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(c->h_tables + 2 * F + ci, c->d_chunktotal + ci, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync((uint32_t*)(c->h_tables + 2 * F + MAX_EN_CHUNKS) + ci, c->d_overflow + ci, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return ICSP_OK;
+}
+
+// after the tables of chunk ci are on the host: enqueue the body copy and fill the caller's tables
+static int body_to_host(icsp_ctx* c, int ci, const icsp_bits_out* out, size_t& dst_off, cudaStream_t s)
+{
+    const auto& ch = c->en_chunks[ci];
+    const size_t F = (size_t)c->cap;
+    if (((uint32_t*)(c->h_tables + 2 * F + MAX_EN_CHUNKS))[ci]) return fail(c, ICSP_ERR_CAPACITY, "bitstream larger than width*height bytes per frame");
+    const size_t total = (size_t)c->h_tables[2 * F + ci];
+    if (dst_off + total > out->cap_bytes) return fail(c, ICSP_ERR_CAPACITY, "icsp_bits_out.cap_bytes too small (%zu needed so far)", dst_off + total);
+    CU(cudaMemcpyAsync(out->bits + dst_off, c->d_bits + ch.region_off, total, cudaMemcpyDeviceToHost, s));
+    for (int i = 0; i < ch.ns; i++) {
+        out->stream_bits[ch.s0 + i] = c->h_tables[ch.s0 + i];
+        out->stream_offset[ch.s0 + i] = dst_off + c->h_tables[F + ch.s0 + i];
+    }
+    dst_off += total;
+    return ICSP_OK;
+}
+
+int icsp_bits_download(icsp_ctx* c, int n_streams, const icsp_bits_out* out)
+{
+    if (!c || !out || !out->bits || !out->stream_bits || !out->stream_offset) return fail(c, ICSP_ERR_PARAM, "icsp_bits_download: bad arguments");
+    if (c->en_chunks.empty()) return fail(c, ICSP_ERR_PARAM, "icsp_bits_download: nothing was entropy coded");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    for (int i = 0; i < (int)c->en_chunks.size(); i++) if ((rc = tables_to_host(c, i, c->stream))) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    size_t dst = 0;
+    for (int i = 0; i < (int)c->en_chunks.size(); i++) if ((rc = body_to_host(c, i, out, dst, c->stream))) return rc;
+    if (out->recon) {
+        const auto& last = c->en_chunks.back();
+        CU(cudaMemcpyAsync(out->recon, c->d_rec, (last.f0 + last.nf) * c->g.fb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    (void)n_streams;
+    return icsp_sync(c);
+}
+
+int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
+                        const icsp_bits_out* out)
+{
+    int rc = check_streams(c, n_streams, gops_per_stream, gop_len);
+    if (rc) return rc;
+    if ((rc = check_run(c, n_streams * gops_per_stream, gop_len, qdc, qac))) return rc;
+    if (!frames || !out || !out->bits || !out->stream_bits || !out->stream_offset) return fail(c, ICSP_ERR_PARAM, "icsp_encode_streams: bad arguments");
+    CU(cudaSetDevice(c->device));
+    if ((rc = entropy_alloc(c))) return rc;
+    const Geom& g = c->g;
+    const int fps = gops_per_stream * gop_len;
+    const int cs = chunk_streams(c, n_streams, gops_per_stream, true);
+    const int nchunks = (n_streams + cs - 1) / cs;
+    c->en_chunks.clear();
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->s_up, c->ev_fork, 0));
+    for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
+    CU(cudaStreamWaitEvent(c->s_down, c->ev_fork, 0));
+    // pass 1: enqueue upload | kernels + entropy | table + recon download for every chunk
+    for (int s0 = 0, i = 0; s0 < n_streams; s0 += cs, i++) {
+        const int ns = std::min(cs, n_streams - s0);
+        const size_t f0 = (size_t)s0 * fps, cnt = (size_t)ns * fps;
+        cudaStream_t st = c->cstream[i % c->n_cstreams];
+        CU(cudaMemcpyAsync(c->d_cur + f0 * g.fb, frames + f0 * g.fb, cnt * g.fb, cudaMemcpyHostToDevice, c->s_up));
+        cudaEvent_t up = chunk_event(c, 3 * i), done = chunk_event(c, 3 * i + 1), tbl = chunk_event(c, 3 * i + 2);
+        CU(cudaEventRecord(up, c->s_up));
+        CU(cudaStreamWaitEvent(st, up, 0));
+        if ((rc = encode_chunk(c, s0 * gops_per_stream, ns * gops_per_stream, gop_len, qdc, qac, st))) return rc;
+        if ((rc = entropy_chunk(c, i, s0, ns, gops_per_stream, gop_len, st))) return rc;
+        if ((rc = tables_to_host(c, i, st))) return rc;
+        CU(cudaEventRecord(done, st));
+        CU(cudaEventRecord(tbl, st));
+        CU(cudaStreamWaitEvent(c->s_down, done, 0));
+        if (out->recon) CU(cudaMemcpyAsync(out->recon + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, c->s_down));
+    }
+    // pass 2: as each chunk's tables arrive, enqueue its body copy (overlaps the kernels of later chunks)
+    size_t dst = 0;
+    for (int i = 0; i < nchunks; i++) {
+        CU(cudaEventSynchronize(chunk_event(c, 3 * i + 2)));
+        if ((rc = body_to_host(c, i, out, dst, c->stream))) { cudaDeviceSynchronize(); return rc; }   // main stream is idle: bodies do not queue behind recon copies
     }
     if ((rc = join_streams(c))) return rc;
     CU(cudaEventRecord(c->ev_join[0], c->s_down));

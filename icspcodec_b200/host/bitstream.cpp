@@ -38,6 +38,14 @@ void BitString::append(const BitString& o)
     else put((uint32_t)o.acc_, o.accbits_);
 }
 
+void BitString::append_msb_bytes(const uint8_t* p, uint64_t nbits)
+{
+    uint64_t i = 0;
+    for (; i + 32 <= nbits; i += 32, p += 4) put(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3], 32);
+    for (; i + 8 <= nbits; i += 8, p++) put(*p, 8);
+    if (i < nbits) put((uint32_t)(*p >> (8 - (nbits - i))), (int)(nbits - i));
+}
+
 std::vector<uint8_t> BitString::reference_body() const
 {
     std::vector<uint8_t> out;
@@ -88,6 +96,19 @@ void encode_frame(BitString& bs, const Syntax& s, int frame, int nmb, bool intra
     }
 }
 
+std::vector<uint8_t> stream_header(const StreamParams& p)
+{
+    std::vector<uint8_t> out(14);
+    // "\0ICSP", u16 height, u16 width, QP_DC, QP_AC, DPCMmode=0, outro (all little endian, packed)
+    out[0] = 0; out[1] = 'I'; out[2] = 'C'; out[3] = 'S'; out[4] = 'P';
+    out[5] = (uint8_t)(p.height & 255); out[6] = (uint8_t)(p.height >> 8);
+    out[7] = (uint8_t)(p.width & 255);  out[8] = (uint8_t)(p.width >> 8);
+    out[9] = (uint8_t)p.qp_dc; out[10] = (uint8_t)p.qp_ac; out[11] = 0;
+    const unsigned outro = ((unsigned)p.intra_period & 63u) << 7;     // 6 bits of intraPeriod, then 7 zero bits
+    out[12] = (uint8_t)(outro & 255); out[13] = (uint8_t)(outro >> 8);
+    return out;
+}
+
 std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_threads)
 {
     const int nmb = (p.width / 16) * (p.height / 16);
@@ -106,14 +127,7 @@ std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_
     BitString all;
     for (auto& f : per_frame) all.append(f);
 
-    std::vector<uint8_t> out(14);
-    // header (ENC.h:201-212 packed, ENC:4901-4922): "\0ICSP", u16 height, u16 width, QP_DC, QP_AC, DPCMmode=0, outro
-    out[0] = 0; out[1] = 'I'; out[2] = 'C'; out[3] = 'S'; out[4] = 'P';
-    out[5] = (uint8_t)(p.height & 255); out[6] = (uint8_t)(p.height >> 8);
-    out[7] = (uint8_t)(p.width & 255);  out[8] = (uint8_t)(p.width >> 8);
-    out[9] = (uint8_t)p.qp_dc; out[10] = (uint8_t)p.qp_ac; out[11] = 0;
-    const unsigned outro = ((unsigned)p.intra_period & 63u) << 7;     // 6 bits of intraPeriod, then 7 zero bits
-    out[12] = (uint8_t)(outro & 255); out[13] = (uint8_t)(outro >> 8);
+    std::vector<uint8_t> out = stream_header(p);
     const std::vector<uint8_t> body = all.reference_body();
     out.insert(out.end(), body.begin(), body.end());
     return out;

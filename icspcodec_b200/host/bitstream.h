@@ -29,6 +29,7 @@ class BitString {
 public:
     void put(uint32_t value, int nbits);      // nbits in [0,32], value's low nbits, MSB first
     void append(const BitString& other);      // bit-level concatenation
+    void append_msb_bytes(const uint8_t* p, uint64_t nbits);   // first nbits bits of an MSB-first byte string
     uint64_t size_bits() const { return nbits_; }
     // bytes of the reference file body: floor(bits/8) full bytes + one last byte holding the tail bits in its LOW
     // bits (the reference shifts bits into each byte from the right and never left-aligns the tail; an extra zero
@@ -47,6 +48,9 @@ void put_vlc(BitString& bs, int v);
 
 // one frame (intra: MPM/mode bits + 6 blocks per MB; inter: mv flag + MVD + 6 blocks per MB)
 void encode_frame(BitString& bs, const Syntax& s, int frame, int nmb, bool intra);
+
+// 14-byte header (ENC.h:201-212 packed, ENC:4901-4922)
+std::vector<uint8_t> stream_header(const StreamParams& p);
 
 // whole stream; frames are entropy coded in parallel (n_threads) and merged in order
 std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_threads);

@@ -27,6 +27,7 @@ struct Options {
     int qdc = 0, qac = 0, ip = 0, threads = 0, gpus = 1;
     int width = 352, height = 288;  // encoder_main.cpp:20 hard-wires CIF; -w/-h are accepted here
     bool recon = true, quiet = false;
+    bool host_entropy = false;  // --host-entropy: download the syntax arrays and entropy-code on the CPU (round-1 path)
 };
 
 void help()
@@ -37,7 +38,8 @@ void help()
            "-n : the number of frames(default is 1)\n-q : QP of DC and AC (16, 8, or 1)\n"
            "--qpdc : QP of DC\n--qpac : QP of AC\n--intraPeriod: period of intra frame(0: All intra)\n"
            "--EnMultiThread: host threads for the entropy coder (0 = all cores)\n"
-           "--gpus: GPUs to shard the GOPs over (default 1)\n--no-recon: do not write test_yuv.yuv\n--help : help message\n");
+           "--gpus: GPUs to shard the GOPs over (default 1)\n--no-recon: do not write test_yuv.yuv\n"
+           "--host-entropy: entropy-code on the CPU instead of the GPU\n--help : help message\n");
 }
 
 bool is_number(const char* s) { return s && *s && strspn(s, "0123456789") == strlen(s); }
@@ -60,6 +62,7 @@ int parse(int argc, char** argv, Options& o)
         else if (a == "--EnMultiThread") { if (!val(o.threads)) return -1; }
         else if (a == "--gpus") { if (!val(o.gpus)) return -1; }
         else if (a == "--no-recon") o.recon = false;
+        else if (a == "--host-entropy") o.host_entropy = true;
         else if (a == "--quiet") o.quiet = true;
         else if (a[0] == '-') { fprintf(stderr, "[ERROR] uncorrect parameters in parsing_command\n"); return -1; }
     }
@@ -71,6 +74,7 @@ struct Shard {          // one GPU's contiguous range of GOPs
     int first_frame = 0, n_gops = 0, gop_len = 0;
     int rc = 0;
     std::string err;
+    std::vector<std::pair<std::vector<uint8_t>, uint64_t>> bits;   // GPU entropy path: MSB-first bit strings, in order
 };
 }  // namespace
 
@@ -99,13 +103,18 @@ int main(int argc, char** argv)
 
     // SoA outputs (pinned)
     const size_t N = (size_t)n * nmb;
-    int16_t* levels = (int16_t*)icsp_host_alloc(N * 384 * 2);
-    uint8_t* acflag = (uint8_t*)icsp_host_alloc(N * 6);
-    uint8_t* mpm = (uint8_t*)icsp_host_alloc(N * 4);
-    uint8_t* ipm = (uint8_t*)icsp_host_alloc(N * 4);
-    int16_t* mvd = (int16_t*)icsp_host_alloc(N * 4);
+    int16_t *levels = nullptr, *mvd = nullptr;
+    uint8_t *acflag = nullptr, *mpm = nullptr, *ipm = nullptr;
+    if (o.host_entropy) {
+        levels = (int16_t*)icsp_host_alloc(N * 384 * 2);
+        acflag = (uint8_t*)icsp_host_alloc(N * 6);
+        mpm = (uint8_t*)icsp_host_alloc(N * 4);
+        ipm = (uint8_t*)icsp_host_alloc(N * 4);
+        mvd = (int16_t*)icsp_host_alloc(N * 4);
+        if (!levels || !acflag || !mpm || !ipm || !mvd) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host)\n"); return 1; }
+    }
     uint8_t* recon = o.recon ? (uint8_t*)icsp_host_alloc((size_t)n * fb) : nullptr;
-    if (!levels || !acflag || !mpm || !ipm || !mvd || (o.recon && !recon)) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host)\n"); return 1; }
+    if (o.recon && !recon) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host)\n"); return 1; }
 
     const auto t0 = std::chrono::steady_clock::now();
     // frame loop: I-frame iff n % intraPeriod == 0 (0 = all intra).  Closed GOPs are independent jobs
@@ -116,9 +125,9 @@ int main(int argc, char** argv)
     std::vector<Shard> shards;
     for (int d = 0; d < G; d++) {
         const int g0 = (int)((long long)full * d / G), g1 = (int)((long long)full * (d + 1) / G);
-        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, ""});
+        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, "", {}});
     }
-    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, ""});
+    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}});
     auto run_shard = [&](Shard& s) {
         const int cnt = s.n_gops * s.gop_len;
         const int per_call_gops = std::max(1, std::min(s.n_gops, 4096 / s.gop_len));   // bound device memory per call
@@ -128,9 +137,22 @@ int main(int argc, char** argv)
         for (int g = 0; g < s.n_gops && !s.rc; g += per_call_gops) {
             const int ng = std::min(per_call_gops, s.n_gops - g);
             const size_t f0 = (size_t)s.first_frame + (size_t)g * s.gop_len;
-            icsp_enc_out out{levels + f0 * nmb * 384, acflag + f0 * nmb * 6, mpm + f0 * nmb * 4, ipm + f0 * nmb * 4,
-                             mvd + f0 * nmb * 2, nullptr, nullptr, recon ? recon + f0 * fb : nullptr};
-            s.rc = icsp_encode_gops(ctx, frames + f0 * fb, ng, s.gop_len, o.qdc, o.qac, &out);
+            if (o.host_entropy) {
+                icsp_enc_out out{levels + f0 * nmb * 384, acflag + f0 * nmb * 6, mpm + f0 * nmb * 4, ipm + f0 * nmb * 4,
+                                 mvd + f0 * nmb * 2, nullptr, nullptr, recon ? recon + f0 * fb : nullptr};
+                s.rc = icsp_encode_gops(ctx, frames + f0 * fb, ng, s.gop_len, o.qdc, o.qac, &out);
+            } else {   // entropy coding + bit packing on the GPU: only bits (and the reconstruction) cross PCIe
+                const size_t cap = (size_t)ng * s.gop_len * ((size_t)o.width * o.height + 32) + 64;
+                std::vector<uint8_t> buf(cap);
+                uint64_t nbits = 0, off = 0;
+                icsp_bits_out bo{buf.data(), cap, &nbits, &off, recon ? recon + f0 * fb : nullptr};
+                s.rc = icsp_encode_streams(ctx, frames + f0 * fb, 1, ng, s.gop_len, o.qdc, o.qac, &bo);
+                if (!s.rc) {
+                    buf.erase(buf.begin(), buf.begin() + (long)off);
+                    buf.resize((size_t)((nbits + 7) / 8));
+                    s.bits.emplace_back(std::move(buf), nbits);
+                }
+            }
             if (s.rc) s.err = icsp_last_error(ctx);
         }
         (void)cnt;
@@ -151,9 +173,20 @@ int main(int argc, char** argv)
 
     icsp_host::StreamParams sp;
     sp.width = o.width; sp.height = o.height; sp.qp_dc = o.qdc; sp.qp_ac = o.qac; sp.intra_period = o.ip; sp.nframes = n;
-    icsp_host::Syntax syn{levels, acflag, mpm, ipm, mvd};
-    const int hw = (int)std::thread::hardware_concurrency();
-    const std::vector<uint8_t> bin = icsp_host::write_stream(sp, syn, o.threads > 0 ? o.threads : std::max(1, hw));
+    std::vector<uint8_t> bin;
+    if (o.host_entropy) {
+        icsp_host::Syntax syn{levels, acflag, mpm, ipm, mvd};
+        const int hw = (int)std::thread::hardware_concurrency();
+        bin = icsp_host::write_stream(sp, syn, o.threads > 0 ? o.threads : std::max(1, hw));
+    } else {   // concatenate the per-shard bit strings in frame order (frames are not byte aligned in the stream, H7)
+        std::sort(shards.begin(), shards.end(), [](const Shard& a, const Shard& b) { return a.first_frame < b.first_frame; });
+        icsp_host::BitString all;
+        for (auto& s : shards)
+            for (auto& seg : s.bits) all.append_msb_bytes(seg.first.data(), seg.second);
+        bin = icsp_host::stream_header(sp);
+        const std::vector<uint8_t> body = all.reference_body();
+        bin.insert(bin.end(), body.begin(), body.end());
+    }
     const auto t2 = std::chrono::steady_clock::now();
 
     char name[512];

@@ -92,6 +92,34 @@ int icsp_enc_upload(icsp_ctx* ctx, const uint8_t* i420_frames, int n_frames);   
 int icsp_enc_run(icsp_ctx* ctx, int n_gops, int gop_len, int qp_dc, int qp_ac);               /* async */
 int icsp_enc_download(icsp_ctx* ctx, int n_frames, const icsp_enc_out* out);                  /* async D2H */
 
+/* ---- encoder with entropy coding + bit packing on the GPU ------------------------- */
+/* Replaces intraPrediction/interPrediction AND intraBody/interBody + DC/AC/MVentropy (ENC:5032-6334) for a batch of
+ * independent streams: stream s = frames [s*gops_per_stream*gop_len, (s+1)*gops_per_stream*gop_len).
+ * Only the packed bitstream bodies (and optionally the reconstruction) cross PCIe, not the int16 levels.
+ *   bits          caller buffer of cap_bytes; stream s's body starts at bits + stream_offset[s] (16-byte aligned) and is
+ *                 an MSB-first bit string of stream_bits[s] bits, zero padded to the next byte.  It is exactly the bit
+ *                 string the reference concatenates in makebitstream (ENC:4873-4895); icsp_finish_body() applies the
+ *                 reference's file rule (bits/8+1 bytes, tail bits right-aligned in the last byte).
+ *   recon         optional [n][fb]; NULL = not copied back.
+ * Returns ICSP_ERR_CAPACITY if cap_bytes is too small (a safe bound is width*height bytes per frame, the size of the
+ * reference's own buffer, ENC:4874). */
+typedef struct icsp_bits_out {
+    uint8_t* bits;
+    size_t cap_bytes;
+    uint64_t* stream_bits;      /* [n_streams] */
+    uint64_t* stream_offset;    /* [n_streams] */
+    uint8_t* recon;
+} icsp_bits_out;
+int icsp_encode_streams(icsp_ctx* ctx, const uint8_t* i420_frames, int n_streams, int gops_per_stream, int gop_len,
+                        int qp_dc, int qp_ac, const icsp_bits_out* out);
+/* Resident variant: entropy-code what icsp_enc_run left on the device (async); results stay on the device until
+ * icsp_bits_download. */
+int icsp_entropy_run(icsp_ctx* ctx, int n_streams, int gops_per_stream, int gop_len);
+int icsp_bits_download(icsp_ctx* ctx, int n_streams, const icsp_bits_out* out);   /* synchronous */
+/* In place: turns an MSB-first body of nbits bits (buffer must hold nbits/8+1 bytes) into the reference's file body;
+ * returns its length nbits/8+1. */
+size_t icsp_finish_body(uint8_t* body, uint64_t nbits);
+
 /* ---- decoder: replaces intraPredictionDecode / interPredictionDecode (double cosine table) -------- */
 int icsp_decode_gops(icsp_ctx* ctx, const icsp_dec_in* in, int n_gops, int gop_len, int qp_dc, int qp_ac,
                      uint8_t* i420_out);

@@ -149,3 +149,38 @@ def test_error_paths(gpu):
         gpu.encode_gops(clip, 1, 2, 0, 8)          # qp must be positive
     with pytest.raises(IcspError):
         gpu.encode_gops(np.zeros((200, gpu.fb), np.uint8), 20, 10, 8, 8)   # over capacity
+
+
+# ---- f1: entropy coding + bit packing on the GPU ---------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c['kind']}-q{c['qdc']}_{c['qac']}-ip{c['ip']}")
+def test_gpu_bitstream_matches_reference(gpu, case):
+    """Bitstream produced entirely on the GPU (icsp_encode_streams) == the reference encoder's .bin, byte for byte."""
+    clip = synth.make_clip(case["kind"], case["nframes"], case["seed"])
+    data, recon = gpu.encode_sequence_bitstream(clip, case["qdc"], case["qac"], case["ip"], want_recon=True)
+    assert len(data) == case["bin_len"]
+    assert md5(data) == case["bin_md5"]
+    assert md5(recon.tobytes()) == case["recon_md5"]
+
+
+def test_gpu_bitstream_stream_batch(gpu, oracle):
+    """A batch of independent streams in one call: every stream's body equals the oracle writer's body of that stream."""
+    clips = [synth.make_clip("highmotion", 10, 500 + i) for i in range(3)] + [synth.make_clip("flat", 10, 7), synth.make_clip("akiyo", 10, 11)]
+    frames = np.concatenate(clips, axis=0)
+    bodies, sbits, _ = gpu.encode_streams(frames, 5, 2, 5, 8, 8)
+    for s, c in enumerate(clips):
+        o = oracle.encode(c, W, H, 8, 8, 5)
+        ref = oracle.write_bitstream(o, W, H, 8, 8, 5)[14:]
+        nb = int(sbits[s])
+        assert len(ref) == nb // 8 + 1
+        got = bytearray(bodies[s].tobytes()) + (b"" if nb % 8 else b"\x00")
+        if nb % 8:
+            got[-1] >>= 8 - nb % 8
+        assert bytes(got) == ref, f"stream {s}"
+    # resident variant: run + entropy_run + bits_download gives the same bodies
+    gpu.upload(frames)
+    gpu.run(10, 5, 8, 8)
+    gpu.entropy_run(5, 2, 5)
+    bodies2, sbits2 = gpu.bits_download(5, frames.shape[0] * (W * H + 32) + 64)
+    assert np.array_equal(sbits, sbits2)
+    for a, b in zip(bodies, bodies2):
+        assert np.array_equal(a, b)
