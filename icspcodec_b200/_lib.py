@@ -37,7 +37,7 @@ EXPORTS = [
     "icsp_set_profiling", "icsp_reset_stats", "icsp_get_stats", "icsp_launch_count",
     "icsp_event_record", "icsp_event_elapsed_ms",
     "icsp_host_alloc", "icsp_host_free",
-    "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body",
+    "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body",
 ]
 
 _lib = None
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     lib.icsp_get_stats.argtypes = [vp, C.POINTER(KernelStat), i]
     lib.icsp_launch_count.argtypes = [vp]
     lib.icsp_launch_count.restype = C.c_uint64
+    lib.icsp_configure.argtypes = [vp, i, i]
     lib.icsp_event_record.argtypes = [vp, i]
     lib.icsp_event_elapsed_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
     lib.icsp_encode_streams.argtypes = [vp, vp, i, i, i, i, i, C.POINTER(BitsOut)]

@@ -272,6 +272,9 @@ class IcspCuda:
         n = self.lib.icsp_get_stats(self.h_ctx, arr, _lib.MAX_KERNELS)
         return {arr[i].name.decode(): dict(launches=int(arr[i].launches), total_ms=float(arr[i].total_ms)) for i in range(max(n, 0))}
 
+    def configure(self, n_compute_streams: int = 2, chunk_gops: int = 0):
+        self._chk(self.lib.icsp_configure(self.h_ctx, n_compute_streams, chunk_gops), "icsp_configure")
+
     def launch_count(self) -> int:
         return int(self.lib.icsp_launch_count(self.h_ctx))
 

@@ -585,6 +585,157 @@ __global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePt
     }
 }
 
+// ---- persistent variant of the speculative (state 0) search ------------------------------------------------------
+// One CTA per (frame, segment) walks DOWN the macroblock rows.  Consecutive rows share 32 of their 48 window rows, so
+// the window lives in a 64-row ring (4 bands of 16 rows, + a 15-row mirror of the ring head so that a candidate's 16
+// rows never wrap) and only the 16 new rows and the next 16 current rows are fetched per step.  The fetch is software
+// pipelined inside every warp: at the top of step r each warp issues the global loads of its share of band r+3 /
+// current rows r+1 into registers, then searches its macroblock of row r (hiding the load latency), then writes the
+// registers to shared memory (ring slot of band r-1, last read at step r-1; current-row buffer (r+1)&1), and one
+// __syncthreads closes the step.
+constexpr int ME_RING_ROWS = 64, ME_MIRROR_ROWS = 15;
+// words per shifted copy of the ring, rounded to a multiple of 32 so that the copy bases keep the bank residues
+// {0,1,1,1} the candidate slot table was built for
+__host__ __device__ inline int me_ring_copy_w(const MeLayout& L) { return ((ME_RING_ROWS + ME_MIRROR_ROWS) * L.pitch_w + 31) & ~31; }
+__host__ __device__ inline size_t me_frame_smem_bytes(const MeLayout& L)
+{
+    return (size_t)(4 * me_ring_copy_w(L) + 8) * 4 + (size_t)2 * 16 * L.seg_mbs * 16;
+}
+
+// store one 16-byte window chunk `v` (chunk index = lane) of padded row prow into the four shifted copies (+ mirror)
+__device__ __forceinline__ void me_store_chunk(const MeLayout& L, uint32_t* s_win, int prow, uint4 v, int lane, int chunks)
+{
+    const int copy_w = me_ring_copy_w(L);
+    const int slot = prow & (ME_RING_ROWS - 1);
+    uint32_t prev = __shfl_up_sync(0xffffffffu, v.w, 1);
+    if (lane == 0) prev = 0;
+    if (lane < chunks) {
+        uint4 o[4];
+        o[0] = v;
+#pragma unroll
+        for (int sft = 1; sft < 4; sft++) {
+            o[sft].x = __funnelshift_r(prev, v.x, 8 * sft);
+            o[sft].y = __funnelshift_r(v.x, v.y, 8 * sft);
+            o[sft].z = __funnelshift_r(v.y, v.z, 8 * sft);
+            o[sft].w = __funnelshift_r(v.z, v.w, 8 * sft);
+        }
+        uint32_t* dst = s_win + slot * L.pitch_w + lane * 4;
+#pragma unroll
+        for (int sft = 0; sft < 4; sft++) *(uint4*)(dst + sft * copy_w) = o[sft];
+        if (slot < ME_MIRROR_ROWS) {
+            dst += ME_RING_ROWS * L.pitch_w;
+#pragma unroll
+            for (int sft = 0; sft < 4; sft++) *(uint4*)(dst + sft * copy_w) = o[sft];
+        }
+    }
+}
+// fetch task `task` of a step: 0..15 = window row of `band`, 16..31 = current row of macroblock row cur_mby
+__device__ __forceinline__ uint4 me_task_load(const Geom& g, const uint8_t* __restrict__ refy, const uint8_t* __restrict__ cury, int task,
+                                              int band, int cur_mby, int m0, int nmbs, int lane)
+{
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (task < 16) { if (lane < nmbs + 2) v = window_chunk(refy, g.w, g.h, band * 16 + task, m0 + lane); }
+    else if (task < 32) { if (lane < nmbs) v = __ldg((const uint4*)(cury + (size_t)(cur_mby * 16 + task - 16) * g.w + (m0 + lane) * 16)); }
+    return v;
+}
+__device__ __forceinline__ void me_task_store(const MeLayout& L, uint32_t* s_win, uint8_t* s_cur, int task, int band, uint4 v, int nmbs, int lane)
+{
+    if (task < 16) me_store_chunk(L, s_win, band * 16 + task, v, lane, nmbs + 2);
+    else if (task < 32) { if (lane < nmbs) *(uint4*)(s_cur + ((task - 16) * L.seg_mbs + lane) * 16) = v; }
+}
+
+// CPITCH / CSEG: compile-time copies of L.pitch_w / L.seg_mbs (0 = use the runtime values).  With constants every
+// shared-memory address of the inner loop is base + immediate, which removes the per-row pointer arithmetic.
+template <int CPITCH, int CSEG>
+__global__ void __launch_bounds__(704) me_sad_frame_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
+{
+    extern __shared__ __align__(16) unsigned char s_me[];
+    const int pitch_w = CPITCH ? CPITCH : L.pitch_w, seg_mbs = CSEG ? CSEG : L.seg_mbs;
+    const int gop = blockIdx.y, seg = blockIdx.x;
+    const int m0 = seg * seg_mbs, nmbs = min(seg_mbs, g.mbw - m0);
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int copy_w = me_ring_copy_w(L);
+    uint32_t* s_win = (uint32_t*)s_me;
+    uint8_t* s_cur0 = s_me + (size_t)(4 * copy_w + 8) * 4;
+    const size_t cur_bytes = (size_t)16 * seg_mbs * 16;
+    const uint8_t* cury = p.cur + f * g.fb;
+    const uint8_t* refy = p.rec + (f - 1) * g.fb;
+
+    // prologue: bands 0..2 and current rows of macroblock row 0
+    for (int band = 0; band < 3; band++)
+        for (int task = warp; task < (band == 0 ? 32 : 16); task += nwarps)
+            me_task_store(L, s_win, s_cur0, task, band, me_task_load(g, refy, cury, task, band, 0, m0, nmbs, lane), nmbs, lane);
+    __syncthreads();
+
+    const int mbl = warp;   // nwarps == nmbs
+    const uint32_t pk0 = __ldg(&g_slot[0][0][lane]), pk1 = __ldg(&g_slot[0][1][lane]);
+    const int idx0 = pk0 & 255, dx0 = (int)(int8_t)(pk0 >> 8), dy0 = (int)(int8_t)(pk0 >> 16);
+    const int idx1 = pk1 & 255, dx1 = (int)(int8_t)(pk1 >> 8), dy1 = (int)(int8_t)(pk1 >> 16);
+    const int col0 = mbl * 16 + 16 + dx0, col1 = mbl * 16 + 16 + dx1;
+    const int off0 = (col0 & 3) * copy_w + ((col0 & 3) ? 1 : 0) + (col0 >> 2);
+    const int off1 = (col1 & 3) * copy_w + ((col1 & 3) ? 1 : 0) + (col1 >> 2);
+    for (int mby = 0; mby < g.mbh; mby++) {
+        const bool more = mby + 1 < g.mbh;
+        uint8_t* s_cur_next = s_cur0 + ((mby + 1) & 1) * cur_bytes;
+        // (1) issue this warp's share of the next step's loads
+        uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
+        if (more) {
+            pre0 = me_task_load(g, refy, cury, warp, mby + 3, mby + 1, m0, nmbs, lane);
+            pre1 = me_task_load(g, refy, cury, warp + nwarps, mby + 3, mby + 1, m0, nmbs, lane);
+        }
+        // (2) search macroblock (mby, m0 + mbl): both candidates of the lane share the current-row loads
+        {
+            const uint4* crow = (const uint4*)(s_cur0 + (mby & 1) * cur_bytes + mbl * 16);
+            // rows slot..slot+15 are contiguous thanks to the mirror
+            const uint32_t* w0 = s_win + off0 + ((mby * 16 + 16 + dy0) & (ME_RING_ROWS - 1)) * pitch_w;
+            const uint32_t* w1 = s_win + off1 + ((mby * 16 + 16 + dy1) & (ME_RING_ROWS - 1)) * pitch_w;
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint4 c = crow[j * seg_mbs];
+                a0 = __vsadu4(w0[j * pitch_w + 0], c.x) + a0;
+                a1 = __vsadu4(w0[j * pitch_w + 1], c.y) + a1;
+                a2 = __vsadu4(w0[j * pitch_w + 2], c.z) + a2;
+                a3 = __vsadu4(w0[j * pitch_w + 3], c.w) + a3;
+                b0 = __vsadu4(w1[j * pitch_w + 0], c.x) + b0;
+                b1 = __vsadu4(w1[j * pitch_w + 1], c.y) + b1;
+                b2 = __vsadu4(w1[j * pitch_w + 2], c.z) + b2;
+                b3 = __vsadu4(w1[j * pitch_w + 3], c.w) + b3;
+            }
+            const uint32_t sad0 = (a0 + a1) + (a2 + a3), sad1 = (b0 + b1) + (b2 + b3);
+            const unsigned zk0 = sad0 == 0 ? (unsigned)idx0 : 64u, zk1 = sad1 == 0 ? (unsigned)idx1 : 64u;
+            const unsigned z1 = __reduce_min_sync(0xffffffffu, min(zk0, zk1));
+            int win = -1, moves = 64;
+            uint32_t best = 0;
+            if (z1 < 64u) {
+                const unsigned z2 = __reduce_min_sync(0xffffffffu, min(zk0 > z1 ? zk0 : 64u, zk1 > z1 ? zk1 : 64u));
+                if (z2 < 64u) { win = (int)z2; moves = win + 1; }
+            }
+            if (win < 0) {
+                const unsigned key = __reduce_min_sync(0xffffffffu, min(sad0 * 64u + idx0, sad1 * 64u + idx1));
+                win = key & 63; best = key >> 6;
+            }
+            if (lane == 0) {
+                const int mb = mby * g.mbw + m0 + mbl;
+                const int wdx = c_cand[0][win][0], wdy = c_cand[0][win][1];
+                *(int*)(p.mv + (f * g.nmb + mb) * 2) = ((-wdx) & 0xffff) | ((-wdy) << 16);
+                p.minsad[f * g.nmb + mb] = (int32_t)best;
+                p.memoves[(size_t)gop * g.nmb + mb] = (uint8_t)moves;
+                if (moves < 64) atomicAdd(&p.meflag[gop], 1u);
+            }
+        }
+        // (3) hand the prefetched rows over; narrow segments (fewer than 16 warps) fetch the rest without overlap
+        if (more) {
+            me_task_store(L, s_win, s_cur_next, warp, mby + 3, pre0, nmbs, lane);
+            me_task_store(L, s_win, s_cur_next, warp + nwarps, mby + 3, pre1, nmbs, lane);
+            for (int task = warp + 2 * nwarps; task < 32; task += nwarps)
+                me_task_store(L, s_win, s_cur_next, task, mby + 3, me_task_load(g, refy, cury, task, mby + 3, mby + 1, m0, nmbs, lane), nmbs, lane);
+        }
+        __syncthreads();
+    }
+}
+
 // Exact fallback, pass 1: for frames where some search broke early, find for every macroblock and every one of
 // the 8 possible start states which visits have SAD == 0 (block identical to the candidate).  The break point
 // of a search depends only on these masks, never on non-zero SAD values.

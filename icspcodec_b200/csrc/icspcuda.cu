@@ -74,7 +74,8 @@ struct icsp_ctx {
     std::vector<cudaEvent_t> free_events;
     cudaEvent_t slots[8] = {};
     char err[256] = "";
-    size_t me_smem = 0, intra_smem = 0, chain_smem = 0;
+    size_t me_smem = 0, me_frame_smem = 0, intra_smem = 0, chain_smem = 0;
+    bool me_persistent = true;
     MeLayout me{};
 };
 
@@ -273,7 +274,13 @@ int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream
     const MeLayout& L = c->me;
     dim3 grid(g.mbh * L.nseg, G);
     const int threads = L.seg_mbs * 32;
-    { LaunchScope ls(c, K_ME_SAD, s); me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0); }
+    {
+        LaunchScope ls(c, K_ME_SAD, s);
+        if (c->me_persistent && L.pitch_w == 104 && L.seg_mbs == 22)   // CIF: compile-time pitch / segment width
+            me_sad_frame_kernel<104, 22><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
+        else if (c->me_persistent) me_sad_frame_kernel<0, 0><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
+        else me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0);
+    }
     { LaunchScope ls(c, K_ME_ZERO, s); me_zero_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st); }
     { LaunchScope ls(c, K_ME_CHAIN, s); me_chain_kernel<<<G, 32, 0, s>>>(g, p); }
     { LaunchScope ls(c, K_ME_FIXUP, s); me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 1); }
@@ -466,6 +473,8 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     if (upload_tables(c) != ICSP_OK) return bail(ICSP_ERR_CUDA);
     c->me = me_layout(g);
     c->me_smem = me_smem_bytes(c->me);
+    c->me_frame_smem = me_frame_smem_bytes(c->me);
+    if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
     c->intra_smem = intra_smem_bytes(g);
     c->chain_smem = (size_t)6 * g.nmb * sizeof(int);
     if (c->me_smem > 200 * 1024 || c->intra_smem > 180 * 1024 || c->chain_smem > 200 * 1024) {
@@ -481,6 +490,9 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
         }
         CUB(cudaFuncSetAttribute(me_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         CUB(cudaFuncSetAttribute(me_zero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<104, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        if ((size_t)optin < c->me_frame_smem) c->me_persistent = false;
         CUB(cudaFuncSetAttribute(intra_luma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
         CUB(cudaFuncSetAttribute(intra_luma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
         CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -915,6 +927,14 @@ int icsp_get_stats(icsp_ctx* c, icsp_kernel_stat* stats, int cap)
     return n;
 }
 uint64_t icsp_launch_count(const icsp_ctx* c) { return c ? c->launches : 0; }
+
+int icsp_configure(icsp_ctx* c, int n_compute_streams, int chunk_gops_)
+{
+    if (!c || n_compute_streams < 1 || n_compute_streams > 4 || chunk_gops_ < 0) return fail(c, ICSP_ERR_PARAM, "icsp_configure: bad arguments");
+    c->n_cstreams = n_compute_streams;
+    c->chunk_gops_target = chunk_gops_;
+    return ICSP_OK;
+}
 
 int icsp_event_record(icsp_ctx* c, int slot)
 {
