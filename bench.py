@@ -239,6 +239,8 @@ def ours(args) -> dict | None:
     build.build()
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

@@ -94,7 +94,7 @@ __device__ __forceinline__ int iz_byte(const uint2& t, int i) { return (int)(((i
 __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
-    __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][64];
+    __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][72];   // 144-byte rows: the 4 groups of a warp land on different banks
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
     const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
     const int item = blockIdx.x * (TR_THREADS / 8) + grp;
@@ -218,8 +218,8 @@ template <int TAB>
 __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
-    __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][64];
-    __shared__ __align__(8) uint8_t s_px[TR_THREADS / 8][64];
+    __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][72];   // 144-byte rows: the 4 groups of a warp land on different banks
+    __shared__ __align__(8) uint8_t s_px[TR_THREADS / 8][72];
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
     const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
     const int item = blockIdx.x * (TR_THREADS / 8) + grp;
@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtr
 // DECODE == 1: mode from (MPM, bit) + reconstruction with the decoder's binary64 table.
 // =====================================================================================================
 constexpr int IW_THREADS = 192;  // 24 block slots per wave step
+#ifndef IW_MIN_CTAS
+#define IW_MIN_CTAS 3
+#endif
 struct IntraSmem {
     uint8_t* bot;    // [bh][w]   bottom row of every block row
     uint8_t* right;  // [bw][h]   right column of every block column
@@ -287,11 +290,11 @@ __host__ __device__ inline size_t intra_smem_bytes(const Geom& g)
 }
 
 template <int DECODE>
-__global__ void __launch_bounds__(IW_THREADS) intra_luma_kernel(Geom g, FramePtrs p, Step st)
+__global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geom g, FramePtrs p, Step st)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ double s_tile[IW_THREADS / 8][72];
-    __shared__ __align__(16) int16_t s_lv[IW_THREADS / 8][64];
+    __shared__ __align__(16) int16_t s_lv[IW_THREADS / 8][72];
     IntraSmem sm;
     sm.dc = (int*)s_raw;
     sm.bot = s_raw + (size_t)g.bh * g.bw * 4;

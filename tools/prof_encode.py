@@ -14,6 +14,7 @@ ap.add_argument("--streams", type=int, default=24)
 ap.add_argument("--frames", type=int, default=100)
 ap.add_argument("--passes", type=int, default=1)
 ap.add_argument("--decode", action="store_true")
+ap.add_argument("--entropy", action="store_true")
 a = ap.parse_args()
 batch = make_batch(a.streams, a.frames, 0)
 n = batch.shape[0]
@@ -22,6 +23,9 @@ ctx.upload(batch)
 for _ in range(a.passes):
     ctx.run(n // 10, 10, 8, 8)
 ctx.sync()
+if a.entropy:
+    ctx.entropy_run(a.streams, a.frames // 10, 10)
+    ctx.sync()
 if a.decode:
     res = ctx.alloc_result(n)
     ctx.download(n, res)
