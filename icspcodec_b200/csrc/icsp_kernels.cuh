@@ -161,9 +161,16 @@ __device__ __forceinline__ void mv_predictor(const int16_t* mv, int mbw, int mb,
     else py = y1 > y2 ? y1 : y2;
 }
 
-__global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step st, int decode)
+// `staged` != 0: the raw DCs (encode) / DC levels (decode) of the plane are first copied to shared memory and the
+// results are written back after the chain, so that the 115 dependent waves touch shared memory only (shared memory:
+// 16 bytes per block; large frames fall back to staged == 0, which reads/writes global memory inside the chain).
+__global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step st, int decode, int staged)
 {
-    extern __shared__ int s_dc[];  // Y[bh*bw], Cb[nmb], Cr[nmb]
+    extern __shared__ __align__(16) unsigned char s_chain[];
+    const int nblk = 6 * g.nmb;
+    int* s_dc = (int*)s_chain;                                   // Y[bh*bw], Cb[nmb], Cr[nmb]
+    double* s_raw = (double*)(s_chain + ((size_t)nblk * 4 + 15) / 16 * 16);   // staged only
+    int* s_lvl = (int*)(s_raw + nblk);                           // staged only: DC level in (decode) / out (encode)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gop = blockIdx.x;
     const size_t f = (size_t)gop * st.gop_len + st.t;
@@ -181,32 +188,47 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step
     }
     if (warp == 0 && st.intra) return;  // intra luma DCs are chained inside the wavefront kernel
     const bool chroma = warp > 0;
-    const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh;
+    const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh, n = bw * bh;
     const int base = chroma ? 4 * g.nmb + (warp - 1) * g.nmb : 0;
     int* dc = s_dc + base;
-    const double* raw = p.dcraw + (size_t)gop * 6 * g.nmb + base;
-    int32_t* rec = p.dcrec + (size_t)gop * 6 * g.nmb + base;
+    const double* raw = p.dcraw + (size_t)gop * nblk + base;
+    int32_t* rec = p.dcrec + (size_t)gop * nblk + base;
     int16_t* lvf = p.levels + f * g.nmb * 384;
+    auto level_slot = [&](int i) -> int16_t* {   // plane-raster block index -> DC slot of its levels row
+        const int by = i / bw, bx = i - by * bw;
+        const int mb = chroma ? i : (by >> 1) * g.mbw + (bx >> 1);
+        const int k = chroma ? 3 + warp : ((by & 1) << 1) | (bx & 1);
+        return lvf + (mb * 6 + k) * 64;
+    };
+    if (staged) {
+        if (decode) for (int i = lane; i < n; i += 32) s_lvl[base + i] = *level_slot(i);
+        else for (int i = lane; i < n; i += 32) s_raw[base + i] = raw[i];
+        __syncwarp();
+    }
     const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
     for (int wv = 0; wv < nwaves; wv++) {
         const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
         for (int by = by_lo + lane; by <= by_hi; by += 32) {
-            const int bx = wv - 2 * by;
+            const int bx = wv - 2 * by, i = by * bw + bx;
             const int P = chroma ? dc_pred_chroma(dc, bw, bx, by) : dc_pred_luma(dc, bw, bx, by);
-            const int mb = chroma ? by * bw + bx : (by >> 1) * g.mbw + (bx >> 1);
-            const int k = chroma ? 3 + warp : ((by & 1) << 1) | (bx & 1);
-            int16_t* dst = lvf + (mb * 6 + k) * 64;
             int L;
-            if (decode) L = *dst;
+            if (decode) L = staged ? s_lvl[base + i] : (int)*level_slot(i);
             else {
-                L = quant(__dsub_rn(raw[by * bw + bx], (double)P), st.qdc, chroma);  // DPCM_DC_block: D -= P (double)
-                *dst = (int16_t)L;
+                // DPCM_DC_block: D -= P (double), then the quantiser
+                L = quant_magic(__dsub_rn(staged ? s_raw[base + i] : raw[i], (double)P), st.magic_dc, chroma);
+                if (staged) s_lvl[base + i] = L; else *level_slot(i) = (int16_t)L;
             }
             const int v = L * st.qdc + P;  // IQuantization + IDPCM_DC_block
-            dc[by * bw + bx] = v;
-            rec[by * bw + bx] = v;
+            dc[i] = v;
+            if (!staged) rec[i] = v;
         }
         __syncwarp();
+    }
+    if (staged) {
+        for (int i = lane; i < n; i += 32) {
+            rec[i] = dc[i];
+            if (!decode) *level_slot(i) = (int16_t)s_lvl[base + i];
+        }
     }
 }
 

@@ -76,6 +76,7 @@ struct icsp_ctx {
     char err[256] = "";
     size_t me_smem = 0, me_frame_smem = 0, intra_smem = 0, chain_smem = 0;
     bool me_persistent = true;
+    int chain_staged = 1;
     MeLayout me{};
 };
 
@@ -304,7 +305,7 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             if (rc) return rc;
         }
         { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 0); }
+        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 0, c->chain_staged); }
         { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0><<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
@@ -325,7 +326,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             LaunchScope ls(c, K_MV_RECON, s);
             mv_recon_kernel<<<G, 32, 0, s>>>(g, p, st);
         }
-        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 1); }
+        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 1, c->chain_staged); }
         { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1><<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
@@ -476,7 +477,8 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     c->me_frame_smem = me_frame_smem_bytes(c->me);
     if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
     c->intra_smem = intra_smem_bytes(g);
-    c->chain_smem = (size_t)6 * g.nmb * sizeof(int);
+    c->chain_smem = (size_t)6 * g.nmb * 16 + 32;      // staged: dc int + raw double + level int per block
+    if (c->chain_smem > 100 * 1024) { c->chain_staged = 0; c->chain_smem = (size_t)6 * g.nmb * sizeof(int) + 32; }
     if (c->me_smem > 200 * 1024 || c->intra_smem > 180 * 1024 || c->chain_smem > 200 * 1024) {
         fail(c, ICSP_ERR_PARAM, "frame %dx%d too large for the shared-memory staging of this build", width, height);
         return bail(ICSP_ERR_PARAM);
