@@ -311,12 +311,15 @@ __host__ __device__ inline size_t intra_smem_bytes(const Geom& g)
     return (size_t)g.bh * g.w + (size_t)g.bw * g.h + (size_t)g.bh * g.bw * 5 + 16;
 }
 
+// `edges` == nullptr: the edge/DC/mode maps live in dynamic shared memory (CIF .. 720x480); otherwise they live in a
+// per-GOP global scratch area of intra_smem_bytes(g) bytes (HD frames; only this CTA touches it, __syncthreads orders it).
 template <int DECODE>
-__global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geom g, FramePtrs p, Step st)
+__global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geom g, FramePtrs p, Step st, unsigned char* edges)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ double s_tile[IW_THREADS / 8][72];
     __shared__ __align__(16) int16_t s_lv[IW_THREADS / 8][72];
+    unsigned char* s_raw = edges ? edges + (size_t)blockIdx.x * ((intra_smem_bytes(g) + 15) / 16 * 16) : s_dyn;
     IntraSmem sm;
     sm.dc = (int*)s_raw;
     sm.bot = s_raw + (size_t)g.bh * g.bw * 4;

@@ -77,6 +77,8 @@ struct icsp_ctx {
     size_t me_smem = 0, me_frame_smem = 0, intra_smem = 0, chain_smem = 0;
     bool me_persistent = true;
     int chain_staged = 1;
+    unsigned char* d_intra_edges = nullptr;   // HD frames: per-GOP edge/DC/mode maps of the intra wavefront in global memory
+    size_t intra_edge_stride = 0;
     MeLayout me{};
 };
 
@@ -299,7 +301,7 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
         dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_ENC, s);
-            intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st);
+            intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
         } else {
             const int rc = launch_me(c, p, st, G, s);
             if (rc) return rc;
@@ -321,7 +323,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
         dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_DEC, s);
-            intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st);
+            intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
         } else {
             LaunchScope ls(c, K_MV_RECON, s);
             mv_recon_kernel<<<G, 32, 0, s>>>(g, p, st);
@@ -479,7 +481,12 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     c->intra_smem = intra_smem_bytes(g);
     c->chain_smem = (size_t)6 * g.nmb * 16 + 32;      // staged: dc int + raw double + level int per block
     if (c->chain_smem > 100 * 1024) { c->chain_staged = 0; c->chain_smem = (size_t)6 * g.nmb * sizeof(int) + 32; }
-    if (c->me_smem > 200 * 1024 || c->intra_smem > 180 * 1024 || c->chain_smem > 200 * 1024) {
+    if (c->intra_smem > 150 * 1024) {   // HD: keep the intra wavefront's maps in global memory (one region per GOP in flight)
+        c->intra_edge_stride = (c->intra_smem + 15) / 16 * 16;
+        CUB(cudaMalloc(&c->d_intra_edges, c->intra_edge_stride * F));
+        c->intra_smem = 0;
+    }
+    if (c->me_smem > 200 * 1024 || c->chain_smem > 200 * 1024) {
         fail(c, ICSP_ERR_PARAM, "frame %dx%d too large for the shared-memory staging of this build", width, height);
         return bail(ICSP_ERR_PARAM);
     }
@@ -521,7 +528,7 @@ void icsp_destroy(icsp_ctx* c)
     for (auto& s : c->slots) if (s) cudaEventDestroy(s);
     void* bufs[] = {c->d_cur, c->d_rec, c->d_levels, c->d_acflag, c->d_mpm, c->d_ipm, c->d_mvd, c->d_mv, c->d_minsad, c->d_dcraw,
                     c->d_dcrec, c->d_mestate, c->d_memoves, c->d_meflag, c->d_mezero, c->d_shim, c->d_blkbits, c->d_framebits,
-                    c->d_streambits, c->d_streamoff, c->d_chunktotal, c->d_overflow, c->d_bits};
+                    c->d_streambits, c->d_streamoff, c->d_chunktotal, c->d_overflow, c->d_bits, c->d_intra_edges};
     if (c->h_tables) cudaFreeHost(c->h_tables);
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -103,7 +103,7 @@ def test_gop_batch_equals_sequential(gpu, oracle):
         assert_syntax_equal(sub, s, what=f"gop {g}: ")
 
 
-@pytest.mark.parametrize("w,h", [(16, 16), (64, 48), (176, 144), (720, 480)])
+@pytest.mark.parametrize("w,h", [(16, 16), (64, 48), (176, 144), (720, 480), (1280, 720), (1920, 1088)])
 def test_other_geometries(oracle, w, h):
     from icspcodec_b200 import IcspCuda
     rng = np.random.default_rng(w * 1000 + h)
@@ -123,6 +123,8 @@ def test_other_geometries(oracle, w, h):
         assert_syntax_equal(res, s, what=f"{w}x{h}: ")
         out = ctx.decode_sequence(res.levels, res.mpm, res.ipm, res.mvd, 8, 4, 4)
         assert np.array_equal(out, oracle.decode(s, w, h, 8, 4, 4))
+        data, _ = ctx.encode_sequence_bitstream(frames, 8, 4, 4)            # GPU entropy path at this geometry
+        assert data == oracle.write_bitstream(s, w, h, 8, 4, 4)
 
 
 def test_roundtrip_properties_full_size(gpu, oracle):
