@@ -542,28 +542,29 @@ __device__ __forceinline__ void me_stage(const Geom& g, const MeLayout& L, uint3
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fixup)
+// rows_per_cta macroblock rows per CTA (blockIdx.x = row group * nseg + segment): 1 for the speculative pass of
+// non-persistent builds, mbh for the fixup pass, so that the usual "nothing to fix" launch is G*nseg cheap CTAs.
+__global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fixup, int rows_per_cta)
 {
     extern __shared__ __align__(16) unsigned char s_me[];
-    const int gop = blockIdx.y, mby = blockIdx.x / L.nseg, seg = blockIdx.x - mby * L.nseg;
+    const int gop = blockIdx.y, rg = blockIdx.x / L.nseg, seg = blockIdx.x - rg * L.nseg;
+    if (fixup && p.meflag[gop] == 0) return;
     const int m0 = seg * L.seg_mbs, nmbs = min(L.seg_mbs, g.mbw - m0);
     const size_t f = (size_t)gop * st.gop_len + st.t;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint8_t* states = p.mestate + (size_t)gop * g.nmb + mby * g.mbw + m0;
-    if (fixup) {
-        if (p.meflag[gop] == 0) return;
-        int any = 0;
-        for (int i = threadIdx.x; i < nmbs; i += blockDim.x) any |= states[i];
-        if (!__syncthreads_or(any)) return;
-    }
     uint32_t* s_win = (uint32_t*)s_me;
     uint8_t* s_cur = s_me + (size_t)(4 * L.copy_w + 8) * 4;
+  for (int mby = rg * rows_per_cta; mby < min(g.mbh, (rg + 1) * rows_per_cta); mby++) {
+    const uint8_t* states = p.mestate + (size_t)gop * g.nmb + mby * g.mbw + m0;
+    if (fixup) {
+        int any = 0;
+        for (int i = threadIdx.x; i < nmbs; i += blockDim.x) any |= states[i];
+        if (!__syncthreads_or(any)) continue;
+    }
     me_stage<true>(g, L, s_win, s_cur, p.cur + f * g.fb, p.rec + (f - 1) * g.fb, mby, m0, nmbs);
-    if (warp >= nmbs) return;
     const int mbl = warp;
-    const int state = fixup ? states[mbl] : 0;
-    if (fixup && state == 0) return;
-
+    const int state = (fixup && warp < nmbs) ? states[mbl] : 0;
+    if (warp < nmbs && !(fixup && state == 0)) {
     uint32_t sad[2];
     int vidx[2];
 #pragma unroll
@@ -611,6 +612,9 @@ __global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePt
             if (moves < 64) atomicAdd(&p.meflag[gop], 1u);
         }
     }
+    }
+    __syncthreads();   // the next row restages the window
+  }
 }
 
 // ---- persistent variant of the speculative (state 0) search ------------------------------------------------------
@@ -768,18 +772,19 @@ __global__ void __launch_bounds__(704) me_sad_frame_kernel(Geom g, MeLayout L, F
 // the 8 possible start states which visits have SAD == 0 (block identical to the candidate).  The break point
 // of a search depends only on these masks, never on non-zero SAD values.
 __global__ void __launch_bounds__(704) me_zero_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
-{
+{   // grid (nseg, G): one CTA per frame segment walks all macroblock rows (it exits at once for unflagged frames)
     extern __shared__ __align__(16) unsigned char s_me[];
-    const int gop = blockIdx.y, mby = blockIdx.x / L.nseg, seg = blockIdx.x - mby * L.nseg;
+    const int gop = blockIdx.y, seg = blockIdx.x;
     if (p.meflag[gop] == 0) return;
     const int m0 = seg * L.seg_mbs, nmbs = min(L.seg_mbs, g.mbw - m0);
     const size_t f = (size_t)gop * st.gop_len + st.t;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* s_win = (uint32_t*)s_me;
     uint8_t* s_cur = s_me + (size_t)(4 * L.copy_w + 8) * 4;
+  for (int mby = 0; mby < g.mbh; mby++) {
     me_stage<false>(g, L, s_win, s_cur, p.cur + f * g.fb, p.rec + (f - 1) * g.fb, mby, m0, nmbs);
-    if (warp >= nmbs) return;
     const int mbl = warp;
+    if (warp < nmbs)
     for (int state = 0; state < 8; state++) {
         unsigned long long z = 0;
 #pragma unroll
@@ -804,6 +809,8 @@ __global__ void __launch_bounds__(704) me_zero_kernel(Geom g, MeLayout L, FrameP
         }
         if (lane == 0) p.mezero[((size_t)gop * g.nmb + mby * g.mbw + m0 + mbl) * 8 + state] = z;
     }
+    __syncthreads();   // the next row restages the window
+  }
 }
 
 // Exact fallback, pass 2: resolve the carried spiral state of every macroblock of a flagged frame.  A search

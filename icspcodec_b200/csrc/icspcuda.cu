@@ -282,11 +282,11 @@ int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream
         if (c->me_persistent && L.pitch_w == 104 && L.seg_mbs == 22)   // CIF: compile-time pitch / segment width
             me_sad_frame_kernel<104, 22><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
         else if (c->me_persistent) me_sad_frame_kernel<0, 0><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
-        else me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0);
+        else me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0, 1);
     }
-    { LaunchScope ls(c, K_ME_ZERO, s); me_zero_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st); }
+    { LaunchScope ls(c, K_ME_ZERO, s); me_zero_kernel<<<dim3(L.nseg, G), threads, c->me_smem, s>>>(g, L, p, st); }
     { LaunchScope ls(c, K_ME_CHAIN, s); me_chain_kernel<<<G, 32, 0, s>>>(g, p); }
-    { LaunchScope ls(c, K_ME_FIXUP, s); me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 1); }
+    { LaunchScope ls(c, K_ME_FIXUP, s); me_sad_kernel<<<dim3(L.nseg, G), threads, c->me_smem, s>>>(g, L, p, st, 1, g.mbh); }
     return ICSP_OK;
 }
 
