@@ -299,7 +299,7 @@ def ours(args) -> dict | None:
     prof_ms = ctx.event_elapsed_ms(4, 5)
     stats = ctx.stats()
     ctx.set_profiling(False)
-    ctx.configure(2, 0)
+    ctx.configure(4, 0)
 
     # ---- value incl. GPU entropy coding (resident) -------------------------------------------------------------
     ctx.entropy_run(args.streams, args.frames // 10, 10)

@@ -44,7 +44,7 @@ struct icsp_ctx {
     cudaStream_t s_up = nullptr, s_down = nullptr;   // H2D / D2H copy streams of the pipelined one-shot calls
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
     std::vector<cudaEvent_t> ev_chunk;      // per-chunk upload / compute-done events
-    int n_cstreams = 2;
+    int n_cstreams = 4;
     int chunk_gops_target = 0;              // 0 = automatic
     // device SoA
     uint8_t *d_cur = nullptr, *d_rec = nullptr, *d_acflag = nullptr, *d_mpm = nullptr, *d_ipm = nullptr;
