@@ -130,7 +130,9 @@ int main(int argc, char** argv)
     if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}});
     auto run_shard = [&](Shard& s) {
         const int cnt = s.n_gops * s.gop_len;
-        const int per_call_gops = std::max(1, std::min(s.n_gops, 4096 / s.gop_len));   // bound device memory per call
+        int call_frames = 4096;                                    // bound device memory per call
+        if (const char* e = getenv("ICSPENC_CALL_FRAMES")) call_frames = std::max(1, atoi(e));
+        const int per_call_gops = std::max(1, std::min(s.n_gops, call_frames / s.gop_len));
         icsp_ctx* ctx = nullptr;
         s.rc = icsp_create(&ctx, s.device, o.width, o.height, per_call_gops * s.gop_len);
         if (s.rc) { s.err = icsp_last_error(nullptr); return; }

@@ -74,6 +74,23 @@ def test_cli_options_and_tail_frames(tmp_path, oracle):
     assert subprocess.run([ENC, "-i", "q_cif.yuv", "-n", "2", "-q", "0"], cwd=tmp_path, capture_output=True).returncode == 1
 
 
+def test_many_device_calls_and_host_entropy(tmp_path):
+    """A sequence larger than one device call: per-call bit strings are concatenated at bit granularity on the host
+    (frames are not byte aligned in the stream); and the --host-entropy path gives the same file."""
+    case = CASES[6]   # highmotion 12 frames ip 30 -> one GOP of 12; use ip 3 -> 4 GOPs, 1 GOP per call
+    clip = synth.make_clip(case["kind"], 12, case["seed"])
+    clip.tofile(tmp_path / "m_cif.yuv")
+    env = dict(os.environ, ICSPENC_CALL_FRAMES="3")
+    subprocess.run([ENC, "-i", "m_cif.yuv", "-n", "12", "-q", "8", "--intraPeriod", "3", "--quiet"], cwd=tmp_path, check=True, env=env)
+    a = open(tmp_path / "m_compCIF_8_8_3.bin", "rb").read()
+    ya = open(tmp_path / "test_yuv.yuv", "rb").read()
+    subprocess.run([ENC, "-i", "m_cif.yuv", "-n", "12", "-q", "8", "--intraPeriod", "3", "--quiet", "--host-entropy"], cwd=tmp_path, check=True)
+    assert open(tmp_path / "m_compCIF_8_8_3.bin", "rb").read() == a
+    assert open(tmp_path / "test_yuv.yuv", "rb").read() == ya
+    subprocess.run([ENC, "-i", "m_cif.yuv", "-n", "12", "-q", "8", "--intraPeriod", "3", "--quiet"], cwd=tmp_path, check=True)
+    assert open(tmp_path / "m_compCIF_8_8_3.bin", "rb").read() == a
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ICSPCodec_O2")), reason="oracle/_ref not on this box")
 def test_live_reference_binaries(tmp_path, oracle):
     clip = synth.make_clip("highmotion", 8, 2025)

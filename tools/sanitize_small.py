@@ -1,0 +1,16 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from icspcodec_b200 import IcspCuda, synth
+clips = [synth.make_clip("highmotion", 4, 4242), synth.make_clip("flat", 4, 7)]
+frames = np.concatenate(clips, axis=0)
+with IcspCuda(352, 288, max_frames=8) as ctx:
+    res = ctx.encode_gops(frames, 2, 4, 8, 8)
+    bodies, sbits, rec = ctx.encode_streams(frames, 2, 1, 4, 8, 8, want_recon=True)
+    out = ctx.decode_gops(res.levels, res.mpm, res.ipm, res.mvd, 2, 4, 8, 8)
+    print("ok", int(sbits.sum()), out.shape)
+with IcspCuda(64, 48, max_frames=4) as ctx:
+    f = np.random.default_rng(0).integers(0, 255, size=(4, 64 * 48 * 3 // 2)).astype(np.uint8)
+    r = ctx.encode_gops(f, 1, 4, 4, 4)
+    print("ok small", r.recon.shape)
