@@ -202,7 +202,7 @@ def reference_arm(args) -> dict:
     value = n_proc * frames * len(times) / total
     return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64+u8", "data": "synthetic", "impl": "reference",
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -355,7 +355,14 @@ def ours(args) -> dict | None:
     for name, s in stats.items():
         if s["launches"] == 0:
             continue
-        frames_k = i_frames if name.startswith("intra_luma") else (p_frames if name.startswith("me_") else p_frames + i_frames)
+        if name.startswith("intra_luma"):
+            frames_k = i_frames
+        elif name.startswith("me_"):
+            frames_k = p_frames
+        elif name.startswith(("fdct", "idct", "dc_chain")):
+            frames_k = p_frames + i_frames / 3.0      # on intra frames these kernels touch the 2 chroma blocks of 6 only
+        else:
+            frames_k = p_frames + i_frames
         ent = {"launches": s["launches"], "total_ms": round(s["total_ms"], 3), "avg_ms": round(s["total_ms"] / s["launches"], 4),
                "share": round(s["total_ms"] / max(1e-9, sum(x["total_ms"] for x in stats.values())), 4)}
         if name in ALG_BYTES and s["total_ms"] > 0:
@@ -369,15 +376,21 @@ def ours(args) -> dict | None:
     dom = max(core, key=lambda k: core[k]["total_ms"])
     d = kernels[dom]
     per_launch_frames = n_gops
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled per launch
+        tj = json.load(open(tpath))
+        if dom in tj:
+            traffic = tj[dom]["dram_bytes_per_frame"] * per_launch_frames
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d.get("alg_GBps"), "peak": peak, "unit": "GB/s",
-                "frac": d.get("hbm_frac"), "traffic": None, "peak_source": peak_src,
+                "frac": d.get("hbm_frac"), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": ALG_BYTES.get(dom, 0) * per_launch_frames, "avg_launch_ms": d["avg_ms"],
                 "timing": f"CUDA events around every launch, {args.steps} serialised steps on one stream ({prof_ms / args.steps:.2f} ms/step incl. entropy coding)",
                 "note": "FP64-issue bound for the DCT/IDCT kernels (strict no-FMA binary64, SURVEY §8d); HBM fraction reported as the contract asks"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64+u8", "data": "synthetic (8 seeded high-motion clips per GPU, each reused 8x with a stream-specific circular shift)",
+            "dtype": "f64", "data": "synthetic (8 seeded high-motion clips per GPU, each reused 8x with a stream-specific circular shift)",
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
