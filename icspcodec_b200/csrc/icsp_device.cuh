@@ -146,13 +146,40 @@ __device__ __forceinline__ int quant_magic(double D, unsigned magic, bool chroma
 }
 
 // ---- 8x8 transforms, one 8-lane group per block --------------------------------------------------
+// costable[u][x] = kTS(u,x) * LIT[kTI(u,x)] with LIT[k] ~ cos(k*pi/16) (ENC.h:191-198): index and sign are compile-time,
+// the seven magnitudes (and irt2) live in REGISTERS (Mags, loaded once per thread through the read-only path) instead
+// of being re-fetched from the constant bank into uniform registers before every FP64 instruction.
+__host__ __device__ constexpr int kTI(int u, int x)
+{
+    int k = ((2 * x + 1) * u) % 32;
+    if (k > 16) k = 32 - k;
+    if (k > 8) k = 16 - k;
+    return k;
+}
+__host__ __device__ constexpr int kTS(int u, int x)
+{
+    int k = ((2 * x + 1) * u) % 32;
+    if (k > 16) k = 32 - k;
+    return k > 8 ? -1 : 1;
+}
+__device__ double g_mag[2][8];   // [table][k]: |costable| magnitudes, table 0 = float widened, 1 = binary64; [t][0] = irt2
+struct Mags { double m[8]; };    // m[0] = irt2, m[1..7] = magnitudes a(1) e(2) b(3) g(4) c(5) f(6) d(7)
+template <int TAB>
+__device__ __forceinline__ Mags load_mags()
+{
+    Mags M;
+#pragma unroll
+    for (int i = 0; i < 8; i++) M.m[i] = __ldg(&g_mag[TAB][i]);
+    return M;
+}
+#define ICSP_T(M, u, x) (kTS(u, x) > 0 ? (M).m[kTI(u, x)] : -(M).m[kTI(u, x)])
+
 // Stage 1 of the forward DCT (ENC:2709-2718) for one row: t[u] = sum_x E[x]*T[u][x].
 // Every term and every partial sum is exactly representable (|E|<=255, 24-bit constants, < 38 bits), so
 // the even/odd factorisation below returns the reference's value bit for bit.
-__device__ __forceinline__ void fdct_row(const int e[8], double t[8])
+__device__ __forceinline__ void fdct_row(const int e[8], double t[8], const Mags& M)
 {
-    const double a = c_T[0][1][0], b = c_T[0][1][1], c = c_T[0][1][2], d = c_T[0][1][3];
-    const double E = c_T[0][2][0], F = c_T[0][2][1], G = c_T[0][4][0];
+    const double a = M.m[1], b = M.m[3], c = M.m[5], d = M.m[7], E = M.m[2], F = M.m[6], G = M.m[4];
     const int s0 = e[0] + e[7], s1 = e[1] + e[6], s2 = e[2] + e[5], s3 = e[3] + e[4];
     const double d0 = (double)(e[0] - e[7]), d1 = (double)(e[1] - e[6]), d2 = (double)(e[2] - e[5]), d3 = (double)(e[3] - e[4]);
     const double p03 = (double)(s0 - s3), p12 = (double)(s1 - s2);
@@ -167,7 +194,7 @@ __device__ __forceinline__ void fdct_row(const int e[8], double t[8])
 }
 // Stage 2 (ENC:2720-2729) for one column u: D[v] = sum_y fl(t[y]*T[v][y]), y ascending, rounded per op;
 // then the irt2 / 0.25 scaling of ENC:2732-2744 (element [0][0] is scaled by irt2 twice, in sequence).
-__device__ __forceinline__ void fdct_col(const double t[8], int u, double D[8])
+__device__ __forceinline__ void fdct_col(const double t[8], int u, double D[8], const Mags& M)
 {
     double s = t[0];
 #pragma unroll
@@ -175,15 +202,15 @@ __device__ __forceinline__ void fdct_col(const double t[8], int u, double D[8])
     D[0] = s;
 #pragma unroll
     for (int v = 1; v < 8; v++) {
-        double acc = __dmul_rn(t[0], c_T[0][v][0]);
+        double acc = __dmul_rn(t[0], ICSP_T(M, v, 0));
 #pragma unroll
-        for (int y = 1; y < 8; y++) acc = __dadd_rn(acc, __dmul_rn(t[y], c_T[0][v][y]));
+        for (int y = 1; y < 8; y++) acc = __dadd_rn(acc, __dmul_rn(t[y], ICSP_T(M, v, y)));
         D[v] = acc;
     }
-    D[0] = __dmul_rn(D[0], c_irt2);
+    D[0] = __dmul_rn(D[0], M.m[0]);
     if (u == 0) {
 #pragma unroll
-        for (int v = 0; v < 8; v++) D[v] = __dmul_rn(D[v], c_irt2);
+        for (int v = 0; v < 8; v++) D[v] = __dmul_rn(D[v], M.m[0]);
     }
 #pragma unroll
     for (int v = 0; v < 8; v++) D[v] = __dmul_rn(D[v], 0.25);
@@ -193,9 +220,9 @@ __device__ __forceinline__ void fdct_col(const double t[8], int u, double D[8])
 // TAB==0: Q[u]*T[u][x] is exact (int x float-widened constant) so an FMA equals mul-then-add;
 // TAB==1 (decoder, binary64 table): the product is inexact and must be rounded separately.
 template <int TAB>
-__device__ __forceinline__ void idct_row(const int q[8], double t[8])
+__device__ __forceinline__ void idct_row(const int q[8], double t[8], const Mags& M)
 {
-    const double a0 = __dmul_rn(c_irt2, (double)q[0]);
+    const double a0 = __dmul_rn(M.m[0], (double)q[0]);
     double qd[8];
 #pragma unroll
     for (int u = 1; u < 8; u++) qd[u] = (double)q[u];
@@ -204,28 +231,33 @@ __device__ __forceinline__ void idct_row(const int q[8], double t[8])
         double s = a0;
 #pragma unroll
         for (int u = 1; u < 8; u++) {
-            if (TAB == 0) s = __fma_rn(qd[u], c_T[0][u][x], s);
-            else s = __dadd_rn(s, __dmul_rn(qd[u], c_T[1][u][x]));
+            if (TAB == 0) s = __fma_rn(qd[u], ICSP_T(M, u, x), s);
+            else s = __dadd_rn(s, __dmul_rn(qd[u], ICSP_T(M, u, x)));
         }
         t[x] = s;
     }
 }
 // Stage 2 (ENC:2869-2878) for one column x: R[y] = sum_v fl((C[v]*t[v])*T[v][y]), then *0.25 (ENC:2885-2891).
-// T[v][7-y] == (-1)^v T[v][y] exactly, so each rounded product serves two outputs.
+// T[v][7-y] == (-1)^v T[v][y] exactly, so each rounded product serves two outputs; rows 2, 4 and 6 of the table hold
+// only 2, 1 and 2 distinct magnitudes in their first four entries, so 21 multiplications (not 28) feed the 56 adds.
 template <int TAB>
-__device__ __forceinline__ void idct_col(const double t[8], double R[8])
+__device__ __forceinline__ void idct_col(const double t[8], double R[8], const Mags& M)
 {
-    const double a0 = __dmul_rn(c_irt2, t[0]);
+    const double a0 = __dmul_rn(M.m[0], t[0]);
     double lo[4], hi[4];
 #pragma unroll
     for (int y = 0; y < 4; y++) lo[y] = hi[y] = a0;
 #pragma unroll
     for (int v = 1; v < 8; v++) {
+        double pm[8];   // product by magnitude index, computed on first use (all indices are compile-time)
+        bool have[8] = {false, false, false, false, false, false, false, false};
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            const double p = __dmul_rn(t[v], c_T[TAB][v][y]);
-            lo[y] = __dadd_rn(lo[y], p);
-            hi[y] = (v & 1) ? __dsub_rn(hi[y], p) : __dadd_rn(hi[y], p);
+            const int k = kTI(v, y);
+            if (!have[k]) { pm[k] = __dmul_rn(t[v], M.m[k]); have[k] = true; }
+            const bool neg = kTS(v, y) < 0;       // fl(a * -m) == -fl(a * m)
+            lo[y] = neg ? __dsub_rn(lo[y], pm[k]) : __dadd_rn(lo[y], pm[k]);
+            hi[y] = (neg != ((v & 1) != 0)) ? __dsub_rn(hi[y], pm[k]) : __dadd_rn(hi[y], pm[k]);
         }
     }
 #pragma unroll

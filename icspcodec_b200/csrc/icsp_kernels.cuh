@@ -39,13 +39,15 @@ struct BlockId {
     int poff;          // plane offset inside a frame
     int dcidx;         // index into dcraw/dcrec (plane-raster order)
 };
-__device__ __forceinline__ BlockId block_id(const Geom& g, int item, int intra)
+// luma launches: item = mb*4 + k ; chroma launches: item = mb*2 + (k-4)
+template <bool CHROMA>
+__device__ __forceinline__ BlockId block_id(const Geom& g, int item)
 {
     BlockId b;
-    if (intra) { b.mb = item >> 1; b.k = 4 + (item & 1); }
-    else { b.mb = item / 6; b.k = item - b.mb * 6; }
+    if (CHROMA) { b.mb = item >> 1; b.k = 4 + (item & 1); }
+    else { b.mb = item >> 2; b.k = item & 3; }
     const int mby = (int)__umulhi((unsigned)b.mb, g.magic_mbw), mbx = b.mb - mby * g.mbw;
-    if (b.k < 4) {
+    if (!CHROMA) {
         b.plane = 0; b.bx = 2 * mbx + (b.k & 1); b.by = 2 * mby + (b.k >> 1);
         b.pw = g.w; b.ph = g.h; b.poff = 0; b.dcidx = b.by * g.bw + b.bx;
     } else {
@@ -72,12 +74,14 @@ __device__ __forceinline__ void pred_row(const Geom& g, const BlockId& b, const 
         ref_row8(prevf + b.poff, g.cw, g.ch, 8, 8 + b.by * 8 + r - my / 2, 8 + b.bx * 8 - mx / 2, out);
 }
 
+template <bool CHROMA>
 __device__ __forceinline__ uint2 pred_row_packed(const Geom& g, const BlockId& b, const uint8_t* prevf, const int16_t* mvf, int r, int intra)
 {
     if (intra) return make_uint2(0u, 0u);
     const int mvw = *(const int*)(mvf + 2 * b.mb);
     const int mx = (int)(int16_t)(mvw & 0xffff), my = mvw >> 16;
-    if (b.plane == 0) return ref_row8_packed(prevf, g.w, g.h, 16, 16 + b.by * 8 + r - my, 16 + b.bx * 8 - mx);
+    // luma: motionCompensation ENC:2185-2186, pad 16; chroma: CmotionCompensation ENC:2538-2539, mv/2 toward zero, pad 8
+    if (!CHROMA) return ref_row8_packed(prevf, g.w, g.h, 16, 16 + b.by * 8 + r - my, 16 + b.bx * 8 - mx);
     return ref_row8_packed(prevf + b.poff, g.cw, g.ch, 8, 8 + b.by * 8 + r - my / 2, 8 + b.bx * 8 - mx / 2);
 }
 
@@ -91,25 +95,27 @@ constexpr int TR_THREADS = 128;  // 16 blocks per CTA
 // Global memory + read-only path: a lane-indexed __constant__ table would serialise 8 ways.
 __device__ uint2 g_izcol[8], g_izrow[8];
 __device__ __forceinline__ int iz_byte(const uint2& t, int i) { return (int)(((i < 4 ? t.x : t.y) >> (8 * (i & 3))) & 255u); }
+template <bool CHROMA>
 __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
     __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][72];   // 144-byte rows: the 4 groups of a warp land on different banks
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-    const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+    const int nitems = (CHROMA ? 2 : 4) * g.nmb;
     const int item = blockIdx.x * (TR_THREADS / 8) + grp;
     const bool valid = item < nitems;
     const int gop = blockIdx.y;
     const size_t f = (size_t)gop * st.gop_len + st.t;
-    const BlockId b = block_id(g, valid ? item : 0, st.intra);
+    const BlockId b = block_id<CHROMA>(g, valid ? item : 0);
     const uint8_t* curf = p.cur + f * g.fb;
     const uint8_t* prevf = p.rec + (f - (st.intra ? 0 : 1)) * g.fb;
+    const Mags M = load_mags<0>();
 
     int e[8];
     const uint2 izc = __ldg(&g_izcol[r]);
     {
         const uint2 cw = __ldg((const uint2*)(curf + b.poff + (size_t)(b.by * 8 + r) * b.pw + b.bx * 8));
-        const uint2 pr = pred_row_packed(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra);
+        const uint2 pr = pred_row_packed<CHROMA>(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             e[i] = (int)((cw.x >> (8 * i)) & 255u) - (int)((pr.x >> (8 * i)) & 255u);
@@ -117,11 +123,11 @@ __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtr
         }
     }
     double t[8], D[8];
-    fdct_row(e, t);
+    fdct_row(e, t, M);
     group_transpose(t, s_tile[grp], r);   // lane r now holds column u=r: t[y][r]
-    fdct_col(t, r, D);                     // D[v][u=r]
+    fdct_col(t, r, D, M);                  // D[v][u=r]
 
-    const bool chroma = b.k >= 4;
+    constexpr bool chroma = CHROMA;
     int nz = 0;
 #pragma unroll
     for (int v = 0; v < 8; v++) {
@@ -236,43 +242,44 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step
 // Kernel C: dequantisation + IDCT + reconstruction (R9, R10, R13).  8 lanes per block.
 // TAB 0: encoder table (float widened) ; TAB 1: decoder table (binary64).
 // =====================================================================================================
-template <int TAB>
+template <int TAB, bool CHROMA>
 __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
     __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][72];   // 144-byte rows: the 4 groups of a warp land on different banks
     __shared__ __align__(8) uint8_t s_px[TR_THREADS / 8][72];
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-    const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
+    const int nitems = (CHROMA ? 2 : 4) * g.nmb;
     const int item = blockIdx.x * (TR_THREADS / 8) + grp;
     const bool valid = item < nitems;
     const int gop = blockIdx.y;
     const size_t f = (size_t)gop * st.gop_len + st.t;
-    const BlockId b = block_id(g, valid ? item : 0, st.intra);
+    const BlockId b = block_id<CHROMA>(g, valid ? item : 0);
     const uint8_t* prevf = p.rec + (f - (st.intra ? 0 : 1)) * g.fb;
+    const Mags M = load_mags<TAB>();
 
     const int16_t* lv = p.levels + ((f * g.nmb + b.mb) * 6 + b.k) * 64;
     *(uint4*)(&s_lv[grp][8 * r]) = __ldg((const uint4*)(lv + 8 * r));
     const uint2 izr = __ldg(&g_izrow[r]);
-    *(uint2*)(&s_px[grp][8 * r]) = pred_row_packed(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra);
+    *(uint2*)(&s_px[grp][8 * r]) = pred_row_packed<CHROMA>(g, b, prevf, p.mv + f * g.nmb * 2, r, st.intra);
     __syncwarp();
     int q[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][iz_byte(izr, u)] * st.qac;   // IQuantization_block
     if (r == 0) q[0] = p.dcrec[(size_t)gop * 6 * g.nmb + b.dcidx];                 // level*QstepDC + P
     double t[8], R[8];
-    idct_row<TAB>(q, t);                  // row y=r
+    idct_row<TAB>(q, t, M);               // row y=r
     group_transpose(t, s_tile[grp], r);   // lane r holds column x=r: t[v][r]
-    idct_col<TAB>(t, R);                  // R[y][x=r]
+    idct_col<TAB>(t, R, M);               // R[y][x=r]
     uint8_t out[8];
 #pragma unroll
     for (int y = 0; y < 8; y++) {
         const int pv = s_px[grp][y * 8 + r];
         int v;
-        if (st.intra) {                      // chroma intra, intraImgReconstruct ENC:1964-1971
+        if (CHROMA && st.intra) {            // chroma intra, intraImgReconstruct ENC:1964-1971
             v = (R[y] > 255.0) ? 255 : __double2int_rz(R[y]);
             v = max(v, 0);
-        } else if (b.plane == 0) {           // mergeBlock ENC:4812 truncates first, interYReconstruct ENC:2343-2346
+        } else if (!CHROMA) {                // mergeBlock ENC:4812 truncates first, interYReconstruct ENC:2343-2346
             v = clip255(pv + __double2int_rz(R[y]));
         } else {                             // interCbCrReconstruct ENC:2605-2607 truncates the double sum
             v = clip255(__double2int_rz(__dadd_rn((double)pv, R[y])));
@@ -334,6 +341,8 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
     const int bw = g.bw, bh = g.bh, w = g.w;
     const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
     const uint2 izc = __ldg(&g_izcol[r]), izr = __ldg(&g_izrow[r]);
+    const Mags M0 = load_mags<0>();
+    const Mags MI = load_mags<TAB>();
 
     for (int wv = 0; wv < nwaves; wv++) {
         const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
@@ -406,9 +415,9 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
             if (r == 0) P = dc_pred_luma(sm.dc, bw, bx, byy);
             if (!DECODE) {
                 double t[8], D[8];
-                fdct_row(e, t);
+                fdct_row(e, t, M0);
                 group_transpose(t, s_tile[grp], r);
-                fdct_col(t, r, D);
+                fdct_col(t, r, D, M0);
                 if (r == 0) D[0] = __dsub_rn(D[0], (double)P);
                 int nz = 0, L[8];
 #pragma unroll
@@ -431,9 +440,9 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
             for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][iz_byte(izr, u)] * ((r == 0 && u == 0) ? st.qdc : st.qac);
             if (r == 0) { q[0] += P; if (active) sm.dc[byy * bw + bx] = q[0]; }
             double t2[8], R[8];
-            idct_row<TAB>(q, t2);
+            idct_row<TAB>(q, t2, MI);
             group_transpose(t2, s_tile[grp], r);
-            idct_col<TAB>(t2, R);   // lane r holds column x=r
+            idct_col<TAB>(t2, R, MI);   // lane r holds column x=r
 
             // IDPCM_pix_0/1/2 (ENC:744-850): (int)(idct + pred) with the sum formed in double, then clipped
             int lefts[8];
@@ -844,9 +853,10 @@ __global__ void dct8x8_kernel(const int32_t* in, double* out, int n)
 #pragma unroll
     for (int i = 0; i < 8; i++) e[i] = in[(size_t)bsafe * 64 + r * 8 + i];
     double t[8], D[8];
-    fdct_row(e, t);
+    const Mags M = load_mags<0>();
+    fdct_row(e, t, M);
     group_transpose(t, s_tile[grp], r);
-    fdct_col(t, r, D);
+    fdct_col(t, r, D, M);
     if (blk < n)
 #pragma unroll
         for (int v = 0; v < 8; v++) out[(size_t)blk * 64 + v * 8 + r] = D[v];
@@ -862,9 +872,10 @@ __global__ void idct8x8_kernel(const int32_t* in, double* out, int n)
 #pragma unroll
     for (int i = 0; i < 8; i++) q[i] = in[(size_t)bsafe * 64 + r * 8 + i];
     double t[8], R[8];
-    idct_row<TAB>(q, t);
+    const Mags M = load_mags<TAB>();
+    idct_row<TAB>(q, t, M);
     group_transpose(t, s_tile[grp], r);
-    idct_col<TAB>(t, R);
+    idct_col<TAB>(t, R, M);
     if (blk < n)
 #pragma unroll
         for (int y = 0; y < 8; y++) out[(size_t)blk * 64 + y * 8 + r] = R[y];

@@ -148,6 +148,14 @@ int upload_tables(icsp_ctx* c)
         }
     }
     CU(cudaMemcpyToSymbol(c_T, T, sizeof(T)));
+    {
+        double mag[2][8];
+        for (int t = 0; t < 2; t++) {
+            mag[t][0] = 1.0 / std::sqrt(2.0);
+            for (int k = 1; k < 8; k++) mag[t][k] = t == 0 ? (double)(float)LIT[k] : LIT[k];
+        }
+        CU(cudaMemcpyToSymbol(g_mag, mag, sizeof(mag)));
+    }
     CU(cudaMemcpyToSymbol(c_irt2, &irt2, sizeof(irt2)));
     CU(cudaMemcpyToSymbol(c_ZZ, ZZ, sizeof(ZZ)));
     CU(cudaMemcpyToSymbol(c_IZ, IZ, sizeof(IZ)));
@@ -297,8 +305,8 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
     for (int t = 0; t < gop_len; t++) {
         Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
-        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
-        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
+        const int per = TR_THREADS / 8;
+        dim3 lgrid((4 * g.nmb + per - 1) / per, G), cgrid((2 * g.nmb + per - 1) / per, G);
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_ENC, s);
             intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
@@ -306,9 +314,11 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             const int rc = launch_me(c, p, st, G, s);
             if (rc) return rc;
         }
-        { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        if (!st.intra) { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
         { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 0, c->chain_staged); }
-        { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0><<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        if (!st.intra) { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0, false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
 }
@@ -319,8 +329,8 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
     for (int t = 0; t < gop_len; t++) {
         Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
-        const int nitems = st.intra ? 2 * g.nmb : 6 * g.nmb;
-        dim3 tgrid((nitems + TR_THREADS / 8 - 1) / (TR_THREADS / 8), G);
+        const int per = TR_THREADS / 8;
+        dim3 lgrid((4 * g.nmb + per - 1) / per, G), cgrid((2 * g.nmb + per - 1) / per, G);
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_DEC, s);
             intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
@@ -329,7 +339,8 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             mv_recon_kernel<<<G, 32, 0, s>>>(g, p, st);
         }
         { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 1, c->chain_staged); }
-        { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1><<<tgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        if (!st.intra) { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1, false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
 }
