@@ -499,14 +499,23 @@ __device__ uint32_t g_slot[8][2][32];
 __host__ __device__ inline int me_copy_off(const MeLayout& L, int s) { return s * L.copy_w + (s ? 1 : 0); }  // +1: see me_stage
 __host__ __device__ inline size_t me_smem_bytes(const MeLayout& L) { return (size_t)(4 * L.copy_w + 8) * 4 + (size_t)16 * L.seg_mbs * 16; }
 
+// sum of absolute differences of the four packed bytes, accumulated: one VABSDIFF4.U8.ACC.  (Written as
+// __vsadu4(a,b)+c the compiler zeroes the accumulator and adds with a separate IADD3 per pair of SADs.)
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ uint4 window_chunk(const uint8_t* __restrict__ plane, int w, int h, int py, int pxc)
 {   // 16 bytes of the padded image (pad 16) at padded row py, padded columns [16*pxc, 16*pxc+16)
     const int PH = h + 32, PW = w + 32;
     if (py == PH - 1) return make_uint4(0, 0, 0, 0);
     const int yy = min(max(py - 16, 0), h - 1);
-    const uint8_t* row = plane + (size_t)yy * w;
+    const uint8_t* row = plane + (unsigned)(yy * w);    // a luma plane is far below 4 GB: 32-bit offsets
     const int x0 = pxc * 16 - 16;
-    if (x0 >= 0 && x0 + 16 <= w) return __ldg((const uint4*)(row + x0));
+    if (x0 >= 0 && x0 + 16 <= w) return __ldg((const uint4*)(row + (unsigned)x0));
     uint32_t v;
     if (x0 < 0) { v = row[0]; v *= 0x01010101u; return make_uint4(v, v, v, v); }
     v = row[w - 1]; v *= 0x01010101u;
@@ -676,7 +685,7 @@ __device__ __forceinline__ uint4 me_task_load(const Geom& g, const uint8_t* __re
 {
     uint4 v = make_uint4(0, 0, 0, 0);
     if (task < 16) { if (lane < nmbs + 2) v = window_chunk(refy, g.w, g.h, band * 16 + task, m0 + lane); }
-    else if (task < 32) { if (lane < nmbs) v = __ldg((const uint4*)(cury + (size_t)(cur_mby * 16 + task - 16) * g.w + (m0 + lane) * 16)); }
+    else if (task < 32) { if (lane < nmbs) v = __ldg((const uint4*)(cury + (unsigned)((cur_mby * 16 + task - 16) * g.w + (m0 + lane) * 16))); }
     return v;
 }
 __device__ __forceinline__ void me_task_store(const MeLayout& L, uint32_t* s_win, uint8_t* s_cur, int task, int band, uint4 v, int nmbs, int lane)
@@ -735,14 +744,14 @@ __global__ void __launch_bounds__(704) me_sad_frame_kernel(Geom g, MeLayout L, F
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const uint4 c = crow[j * seg_mbs];
-                a0 = __vsadu4(w0[j * pitch_w + 0], c.x) + a0;
-                a1 = __vsadu4(w0[j * pitch_w + 1], c.y) + a1;
-                a2 = __vsadu4(w0[j * pitch_w + 2], c.z) + a2;
-                a3 = __vsadu4(w0[j * pitch_w + 3], c.w) + a3;
-                b0 = __vsadu4(w1[j * pitch_w + 0], c.x) + b0;
-                b1 = __vsadu4(w1[j * pitch_w + 1], c.y) + b1;
-                b2 = __vsadu4(w1[j * pitch_w + 2], c.z) + b2;
-                b3 = __vsadu4(w1[j * pitch_w + 3], c.w) + b3;
+                a0 = sad4_acc(w0[j * pitch_w + 0], c.x, a0);
+                a1 = sad4_acc(w0[j * pitch_w + 1], c.y, a1);
+                a2 = sad4_acc(w0[j * pitch_w + 2], c.z, a2);
+                a3 = sad4_acc(w0[j * pitch_w + 3], c.w, a3);
+                b0 = sad4_acc(w1[j * pitch_w + 0], c.x, b0);
+                b1 = sad4_acc(w1[j * pitch_w + 1], c.y, b1);
+                b2 = sad4_acc(w1[j * pitch_w + 2], c.z, b2);
+                b3 = sad4_acc(w1[j * pitch_w + 3], c.w, b3);
             }
             const uint32_t sad0 = (a0 + a1) + (a2 + a3), sad1 = (b0 + b1) + (b2 + b3);
             const unsigned zk0 = sad0 == 0 ? (unsigned)idx0 : 64u, zk1 = sad1 == 0 ? (unsigned)idx1 : 64u;
