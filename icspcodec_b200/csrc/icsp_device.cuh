@@ -111,23 +111,26 @@ __device__ __forceinline__ uint2 ref_row8_packed(const uint8_t* __restrict__ P, 
 }
 
 // ---- A.5 DC predictors on the 8x8 grid of one plane (dc = reconstructed DCs, row-major [bh][bw]) ----
+// S = element stride of the map in ints (2 when the DC shares an 8-byte slot with the level, see dc_chain_kernel)
+template <int S = 1>
 __device__ __forceinline__ int dc_pred_luma(const int* dc, int bw, int bx, int by)
 {  // ENC:3643-3990 reduced to geometry
     if (bx == 0 && by == 0) return 1024;
-    if (by == 0) return dc[bx - 1];
-    if (bx == 0) return dc[(by - 1) * bw];
-    const int L = dc[by * bw + bx - 1], U = dc[(by - 1) * bw + bx];
-    if ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1)) return med3(L, U, dc[(by - 1) * bw + bx + 1]);
-    return med3(L, dc[(by - 1) * bw + bx - 1], U);
+    if (by == 0) return dc[S * (bx - 1)];
+    if (bx == 0) return dc[S * ((by - 1) * bw)];
+    const int L = dc[S * (by * bw + bx - 1)], U = dc[S * ((by - 1) * bw + bx)];
+    if ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1)) return med3(L, U, dc[S * ((by - 1) * bw + bx + 1)]);
+    return med3(L, dc[S * ((by - 1) * bw + bx - 1)], U);
 }
+template <int S = 1>
 __device__ __forceinline__ int dc_pred_chroma(const int* dc, int bw, int bx, int by)
 {  // ENC:4482-4513
     if (bx == 0 && by == 0) return 1024;
-    if (by == 0) return dc[bx - 1];
-    if (bx == 0) return dc[(by - 1) * bw];
-    const int L = dc[by * bw + bx - 1], U = dc[(by - 1) * bw + bx];
-    if (bx == bw - 1) return med3(L, dc[(by - 1) * bw + bx - 1], U);
-    return med3(L, U, dc[(by - 1) * bw + bx + 1]);
+    if (by == 0) return dc[S * (bx - 1)];
+    if (bx == 0) return dc[S * ((by - 1) * bw)];
+    const int L = dc[S * (by * bw + bx - 1)], U = dc[S * ((by - 1) * bw + bx)];
+    if (bx == bw - 1) return med3(L, dc[S * ((by - 1) * bw + bx - 1)], U);
+    return med3(L, U, dc[S * ((by - 1) * bw + bx + 1)]);
 }
 
 // ---- quantiser (A.4) ----------------------------------------------------------------------------

@@ -167,16 +167,15 @@ __device__ __forceinline__ void mv_predictor(const int16_t* mv, int mbw, int mb,
     else py = y1 > y2 ? y1 : y2;
 }
 
-// `staged` != 0: the raw DCs (encode) / DC levels (decode) of the plane are first copied to shared memory and the
-// results are written back after the chain, so that the 115 dependent waves touch shared memory only (shared memory:
-// 16 bytes per block; large frames fall back to staged == 0, which reads/writes global memory inside the chain).
+// `staged` != 0: every block owns one 8-byte shared-memory slot that first holds its input (raw DC as a double when
+// encoding, DC level when decoding) and, once the chain has passed, {reconstructed DC, DC level}; the 115 dependent
+// waves then touch shared memory only and the results are written back at the end (8 bytes per block of shared
+// memory: 19 KB for CIF, so ~11 frames are resident per SM).  Large frames fall back to staged == 0 (int map only,
+// inputs/outputs in global memory inside the chain).
 __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step st, int decode, int staged)
 {
     extern __shared__ __align__(16) unsigned char s_chain[];
     const int nblk = 6 * g.nmb;
-    int* s_dc = (int*)s_chain;                                   // Y[bh*bw], Cb[nmb], Cr[nmb]
-    double* s_raw = (double*)(s_chain + ((size_t)nblk * 4 + 15) / 16 * 16);   // staged only
-    int* s_lvl = (int*)(s_raw + nblk);                           // staged only: DC level in (decode) / out (encode)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gop = blockIdx.x;
     const size_t f = (size_t)gop * st.gop_len + st.t;
@@ -196,7 +195,6 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step
     const bool chroma = warp > 0;
     const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh, n = bw * bh;
     const int base = chroma ? 4 * g.nmb + (warp - 1) * g.nmb : 0;
-    int* dc = s_dc + base;
     const double* raw = p.dcraw + (size_t)gop * nblk + base;
     int32_t* rec = p.dcrec + (size_t)gop * nblk + base;
     int16_t* lvf = p.levels + f * g.nmb * 384;
@@ -206,35 +204,49 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step
         const int k = chroma ? 3 + warp : ((by & 1) << 1) | (bx & 1);
         return lvf + (mb * 6 + k) * 64;
     };
-    if (staged) {
-        if (decode) for (int i = lane; i < n; i += 32) s_lvl[base + i] = *level_slot(i);
-        else for (int i = lane; i < n; i += 32) s_raw[base + i] = raw[i];
-        __syncwarp();
-    }
     const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
+    if (staged) {
+        double* slot = (double*)s_chain + base;          // 8 bytes per block
+        int* dc2 = (int*)slot;                           // {dc, level} pairs: dc at even ints
+        if (decode) for (int i = lane; i < n; i += 32) dc2[2 * i + 1] = *level_slot(i);
+        else for (int i = lane; i < n; i += 32) slot[i] = raw[i];
+        __syncwarp();
+        for (int wv = 0; wv < nwaves; wv++) {
+            const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
+            for (int by = by_lo + lane; by <= by_hi; by += 32) {
+                const int bx = wv - 2 * by, i = by * bw + bx;
+                const int P = chroma ? dc_pred_chroma<2>(dc2, bw, bx, by) : dc_pred_luma<2>(dc2, bw, bx, by);
+                int L;
+                if (decode) L = dc2[2 * i + 1];
+                else L = quant_magic(__dsub_rn(slot[i], (double)P), st.magic_dc, chroma);   // DPCM_DC_block: D -= P, then quantise
+                *(int2*)(dc2 + 2 * i) = make_int2(L * st.qdc + P, L);                      // IQuantization + IDPCM_DC_block
+            }
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) {
+            const int2 v = *(const int2*)(dc2 + 2 * i);
+            rec[i] = v.x;
+            if (!decode) *level_slot(i) = (int16_t)v.y;
+        }
+        return;
+    }
+    int* dc = (int*)s_chain + base;                      // Y[bh*bw], Cb[nmb], Cr[nmb]
     for (int wv = 0; wv < nwaves; wv++) {
         const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
         for (int by = by_lo + lane; by <= by_hi; by += 32) {
             const int bx = wv - 2 * by, i = by * bw + bx;
             const int P = chroma ? dc_pred_chroma(dc, bw, bx, by) : dc_pred_luma(dc, bw, bx, by);
             int L;
-            if (decode) L = staged ? s_lvl[base + i] : (int)*level_slot(i);
+            if (decode) L = (int)*level_slot(i);
             else {
-                // DPCM_DC_block: D -= P (double), then the quantiser
-                L = quant_magic(__dsub_rn(staged ? s_raw[base + i] : raw[i], (double)P), st.magic_dc, chroma);
-                if (staged) s_lvl[base + i] = L; else *level_slot(i) = (int16_t)L;
+                L = quant_magic(__dsub_rn(raw[i], (double)P), st.magic_dc, chroma);
+                *level_slot(i) = (int16_t)L;
             }
-            const int v = L * st.qdc + P;  // IQuantization + IDPCM_DC_block
+            const int v = L * st.qdc + P;
             dc[i] = v;
-            if (!staged) rec[i] = v;
+            rec[i] = v;
         }
         __syncwarp();
-    }
-    if (staged) {
-        for (int i = lane; i < n; i += 32) {
-            rec[i] = dc[i];
-            if (!decode) *level_slot(i) = (int16_t)s_lvl[base + i];
-        }
     }
 }
 
