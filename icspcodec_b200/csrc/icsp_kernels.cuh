@@ -206,16 +206,25 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step
     };
     const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
     if (staged) {
-        double* slot = (double*)s_chain + base;          // 8 bytes per block
+        // slots: luma n+1, Cb nmb+1, Cr nmb+1 (the +1 is a sentinel holding 1024, the predictor of the first block)
+        double* slot = (double*)s_chain + base + warp;   // 8 bytes per block
         int* dc2 = (int*)slot;                           // {dc, level} pairs: dc at even ints
         if (decode) for (int i = lane; i < n; i += 32) dc2[2 * i + 1] = *level_slot(i);
         else for (int i = lane; i < n; i += 32) slot[i] = raw[i];
+        if (lane == 0) dc2[2 * n] = 1024;
         __syncwarp();
         for (int wv = 0; wv < nwaves; wv++) {
             const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
             for (int by = by_lo + lane; by <= by_hi; by += 32) {
                 const int bx = wv - 2 * by, i = by * bw + bx;
-                const int P = chroma ? dc_pred_chroma<2>(dc2, bw, bx, by) : dc_pred_luma<2>(dc2, bw, bx, by);
+                // A.5 without divergent branches: the three neighbours whose median is the predictor (single-neighbour
+                // cases repeat that neighbour; the first block reads the sentinel); med3 is a true median (ENC:3677-3679)
+                const bool ur = chroma ? (bx != bw - 1) : ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1));
+                int a = i - 1, b = i - bw, c = ur ? i - bw + 1 : i - bw - 1;
+                if (by == 0) { a = bx == 0 ? n : i - 1; b = a; c = a; }
+                else if (bx == 0) { a = b; c = b; }
+                const int va = dc2[2 * a], vb = dc2[2 * b], vc = dc2[2 * c];
+                const int P = max(min(va, vb), min(max(va, vb), vc));
                 int L;
                 if (decode) L = dc2[2 * i + 1];
                 else L = quant_magic(__dsub_rn(slot[i], (double)P), st.magic_dc, chroma);   // DPCM_DC_block: D -= P, then quantise
@@ -424,7 +433,15 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
             int16_t* lv = p.levels + ((f * g.nmb + mb) * 6 + k) * 64;
             int q[8];  // dequantised coefficients of ROW r after the transposition below
             int P = 0;
-            if (r == 0) P = dc_pred_luma(sm.dc, bw, bx, byy);
+            if (r == 0) {   // A.5, branch free (the four groups of a warp would otherwise serialise on different cases)
+                const int i = byy * bw + bx;
+                const bool ur = (bx & 1) == 0 || ((byy & 1) == 0 && bx != bw - 1);
+                int a = i - 1, b = i - bw, c2 = ur ? i - bw + 1 : i - bw - 1;
+                if (byy == 0) { a = bx == 0 ? 0 : i - 1; b = a; c2 = a; }
+                else if (bx == 0) { a = b; c2 = b; }
+                const int va = sm.dc[a], vb = sm.dc[b], vc = sm.dc[c2];
+                P = (bx == 0 && byy == 0) ? 1024 : max(min(va, vb), min(max(va, vb), vc));
+            }
             if (!DECODE) {
                 double t[8], D[8];
                 fdct_row(e, t, M0);

@@ -490,7 +490,7 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     c->me_frame_smem = me_frame_smem_bytes(c->me);
     if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
     c->intra_smem = intra_smem_bytes(g);
-    c->chain_smem = (size_t)6 * g.nmb * 8 + 32;       // staged: one 8-byte slot per block
+    c->chain_smem = (size_t)(6 * g.nmb + 3) * 8 + 32;  // staged: one 8-byte slot per block + a sentinel per plane
     if (c->chain_smem > 100 * 1024) { c->chain_staged = 0; c->chain_smem = (size_t)6 * g.nmb * sizeof(int) + 32; }
     if (c->intra_smem > 150 * 1024) {   // HD: keep the intra wavefront's maps in global memory (one region per GOP in flight)
         c->intra_edge_stride = (c->intra_smem + 15) / 16 * 16;
