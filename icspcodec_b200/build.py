@@ -32,6 +32,17 @@ def _stale(target: str, sources: list[str]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Idempotent and safe under several ranks starting at once (file lock)."""
+    import fcntl
+    with open(os.path.join(PKG, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "icspcuda.h")]
     if force or _stale(LIB, srcs):
         cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "icspcuda.cu")]

@@ -181,6 +181,14 @@ struct BitSink {
 
 __global__ void __launch_bounds__(EN_THREADS) entropy_pack_kernel(Geom g, FramePtrs p, EntropyPtrs e, int gop_len, int frames_per_stream)
 {
+    // (len << 16 | code) of every level in [-31, 31]: almost all symbols; larger ones take the arithmetic path
+    __shared__ uint32_t s_vlc[64];
+    if (threadIdx.x < 63) { int len; const uint32_t c = vlc_code((int)threadIdx.x - 31, len); s_vlc[threadIdx.x] = ((uint32_t)len << 16) | c; }
+    __syncthreads();
+    auto put_level = [&](BitSink& sk, int v) {
+        if ((unsigned)(v + 31) < 63u) { const uint32_t t = s_vlc[v + 31]; sk.put(t & 0xffffu, (int)(t >> 16)); }
+        else { int len; const uint32_t c = vlc_code(v, len); sk.put(c, len); }
+    };
     const int nblk = g.nmb * 6;
     const int idx = blockIdx.x * EN_THREADS + threadIdx.x;
     if (idx >= nblk || *e.overflow) return;
@@ -218,8 +226,9 @@ __global__ void __launch_bounds__(EN_THREADS) entropy_pack_kernel(Geom g, FrameP
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (!(i == 0 && j == 0)) { code = vlc_code((int)(int16_t)(w[j] & 0xffffu), len); sink.put(code, len); }
-                code = vlc_code((int)(int16_t)(w[j] >> 16), len); sink.put(code, len);
+                if (w[j] == 0u && !(i == 0 && j == 0)) { sink.put(0u, 4); continue; }     // two zero levels: "00" "00"
+                if (!(i == 0 && j == 0)) put_level(sink, (int)(int16_t)(w[j] & 0xffffu));
+                put_level(sink, (int)(int16_t)(w[j] >> 16));
             }
         }
     }
