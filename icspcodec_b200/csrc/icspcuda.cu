@@ -22,13 +22,15 @@ thread_local char g_create_error[256] = "";
 
 enum KernelId {
     K_INTRA_ENC = 0, K_INTRA_DEC, K_FDCT, K_DCCHAIN, K_IDCT_ENC, K_IDCT_DEC, K_ME_SAD, K_ME_ZERO, K_ME_CHAIN, K_ME_FIXUP,
-    K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_EN_SIZE, K_EN_FSCAN, K_EN_SSCAN, K_EN_ZERO, K_EN_PACK, K_COUNT
+    K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_EN_SIZE, K_EN_FSCAN, K_EN_SSCAN, K_EN_ZERO, K_EN_PACK, K_FDCT_C, K_IDCT_ENC_C,
+    K_IDCT_DEC_C, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "intra_luma_kernel<enc>", "intra_luma_kernel<dec>", "fdct_quant_kernel", "dc_chain_kernel", "idct_recon_kernel<enc>",
     "idct_recon_kernel<dec>", "me_sad_kernel", "me_zero_kernel", "me_chain_kernel", "me_sad_kernel(fixup)",
     "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel", "entropy_size_kernel", "entropy_frame_scan_kernel",
-    "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel"};
+    "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel", "fdct_quant_kernel<chroma>",
+    "idct_recon_kernel<enc,chroma>", "idct_recon_kernel<dec,chroma>"};
 
 struct Pending { int k; cudaEvent_t a, b; };
 
@@ -315,10 +317,10 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             if (rc) return rc;
         }
         if (!st.intra) { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, K_FDCT_C, s); fdct_quant_kernel<true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
         { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 0, c->chain_staged); }
         if (!st.intra) { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0, false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, K_IDCT_ENC_C, s); idct_recon_kernel<0, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
 }
@@ -340,7 +342,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
         }
         { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 1, c->chain_staged); }
         if (!st.intra) { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1, false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, K_IDCT_DEC_C, s); idct_recon_kernel<1, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
 }
