@@ -20,11 +20,6 @@ struct Geom {
     unsigned magic_bw, magic_mbw;  // ceil(2^32/bw), ceil(2^32/mbw): n/d == umulhi(n, magic) while n*d < 2^32
 };
 
-// costable[u][x]: table 0 = encoder (binary32 literals widened, ENC.h:190-198), 1 = decoder (binary64, DEC.h:19-27)
-__constant__ double c_T[2][8][8];
-__constant__ double c_irt2;                 // 1.0/sqrt(2.0)  (ENC.h:199)
-__constant__ unsigned char c_ZZ[64];        // zig-zag position k -> raster index (ENC:3031-3094)
-__constant__ unsigned char c_IZ[64];        // raster index -> zig-zag position
 __constant__ signed char c_cand[8][64][2];  // spiral visiting order per carried start state: (dx,dy) (ENC:2101-2143)
 __constant__ unsigned char c_next[8][65];   // start state, moves made -> state handed to the next macroblock
 
@@ -67,29 +62,8 @@ __device__ __forceinline__ int ref_px(const uint8_t* __restrict__ P, int w, int 
     return P[yy * w + xx];
 }
 
-// 8 consecutive prediction pixels of one row, starting at padded coordinate (y, x0).
-__device__ __forceinline__ void ref_row8(const uint8_t* __restrict__ P, int w, int h, int pad, int y, int x0, int out[8])
-{
-    const int ux = x0 - pad, uy = y - pad;
-    if (uy >= 0 && uy < h && ux >= 0 && ux + 7 < w) {  // interior: no clamping, no zero row/col
-        const uint8_t* p = P + uy * w + ux;
-        const uintptr_t a = (uintptr_t)p;
-        const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
-        const int sh = (int)(a & 3) * 8;
-        uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = sh ? __ldg(q + 2) : 0u;
-        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            out[i] = (lo >> (8 * i)) & 255;
-            out[4 + i] = (hi >> (8 * i)) & 255;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) out[i] = ref_px(P, w, h, pad, y, x0 + i);
-    }
-}
-
-// the same 8 pixels packed as two little-endian words (byte i of the pair = pixel x0+i)
+// 8 consecutive prediction pixels of one row, starting at padded coordinate (y, x0), packed as two little-endian
+// words (byte i of the pair = pixel x0+i)
 __device__ __forceinline__ uint2 ref_row8_packed(const uint8_t* __restrict__ P, int w, int h, int pad, int y, int x0)
 {
     const int ux = x0 - pad, uy = y - pad;
@@ -135,12 +109,6 @@ __device__ __forceinline__ int dc_pred_chroma(const int* dc, int bw, int bx, int
 
 // ---- quantiser (A.4) ----------------------------------------------------------------------------
 // luma ENC:2780  (int)(D+0.5)/Q ; chroma ENC:4642  (int)floor(D+0.5)/Q ; both divisions truncate toward zero
-__device__ __forceinline__ int quant(double D, int Q, bool chroma)
-{
-    const double x = __dadd_rn(D, 0.5);
-    const int r = chroma ? __double2int_rd(x) : __double2int_rz(x);
-    return r / Q;
-}
 __device__ __forceinline__ int quant_magic(double D, unsigned magic, bool chroma)
 {
     const double x = __dadd_rn(D, 0.5);

@@ -58,22 +58,8 @@ __device__ __forceinline__ BlockId block_id(const Geom& g, int item)
     return b;
 }
 
-// prediction row r of a block (inter: motion compensated from the previous reconstruction; intra chroma: 0)
-__device__ __forceinline__ void pred_row(const Geom& g, const BlockId& b, const uint8_t* prevf, const int16_t* mvf, int r,
-                                         int intra, int out[8])
-{
-    if (intra) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) out[i] = 0;
-        return;
-    }
-    const int mx = mvf[2 * b.mb], my = mvf[2 * b.mb + 1];
-    if (b.plane == 0)  // motionCompensation ENC:2185-2186: ref = origin - mv + pad
-        ref_row8(prevf, g.w, g.h, 16, 16 + b.by * 8 + r - my, 16 + b.bx * 8 - mx, out);
-    else               // CmotionCompensation ENC:2538-2539: mv/2 truncates toward zero, pad 8
-        ref_row8(prevf + b.poff, g.cw, g.ch, 8, 8 + b.by * 8 + r - my / 2, 8 + b.bx * 8 - mx / 2, out);
-}
-
+// prediction row r of a block, 8 pixels packed in two words (inter: motion compensated from the previous
+// reconstruction; intra chroma: 0)
 template <bool CHROMA>
 __device__ __forceinline__ uint2 pred_row_packed(const Geom& g, const BlockId& b, const uint8_t* prevf, const int16_t* mvf, int r, int intra)
 {

@@ -115,20 +115,7 @@ int geom_init(Geom& g, int w, int h)
 int upload_tables(icsp_ctx* c)
 {
     static const double LIT[8] = {1.0, 0.980785, 0.92388, 0.83147, 0.707107, 0.55557, 0.382683, 0.19509};
-    double T[2][8][8];
-    // costable[u][x] ~ cos((2x+1)u*pi/16) as 6-digit literals (ENC.h:191-198 / DEC.h:20-27): pick literal by angle
-    for (int u = 0; u < 8; u++)
-        for (int x = 0; x < 8; x++) {
-            int k = ((2 * x + 1) * u) % 32;       // angle k*pi/16, period 32
-            int sgn = 1;
-            if (k > 16) k = 32 - k;               // cos(2pi - a) = cos a
-            if (k > 8) { k = 16 - k; sgn = -1; }  // cos(pi - a) = -cos a
-            // k in [0,8]; k == 8 never occurs for odd (2x+1)*u multiples except u==0 handled by k==0
-            double lit = (k == 8) ? 0.0 : LIT[k];
-            T[1][u][x] = sgn * lit;
-            T[0][u][x] = (double)(float)(sgn * lit);
-        }
-    const double irt2 = 1.0 / std::sqrt(2.0);
+    // costable[u][x] = sign * LIT[k] with k = angle index (kTI/kTS in icsp_device.cuh); only the 7 magnitudes are uploaded
     static const unsigned char ZZ[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                          41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                          30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
@@ -149,18 +136,14 @@ int upload_tables(icsp_ctx* c)
             next[s][it + 1] = (unsigned char)(flag | (xflag < 0 ? 2 : 0) | (yflag > 0 ? 4 : 0));
         }
     }
-    CU(cudaMemcpyToSymbol(c_T, T, sizeof(T)));
     {
         double mag[2][8];
         for (int t = 0; t < 2; t++) {
-            mag[t][0] = 1.0 / std::sqrt(2.0);
+            mag[t][0] = 1.0 / std::sqrt(2.0);   // irt2 (ENC.h:199)
             for (int k = 1; k < 8; k++) mag[t][k] = t == 0 ? (double)(float)LIT[k] : LIT[k];
         }
         CU(cudaMemcpyToSymbol(g_mag, mag, sizeof(mag)));
     }
-    CU(cudaMemcpyToSymbol(c_irt2, &irt2, sizeof(irt2)));
-    CU(cudaMemcpyToSymbol(c_ZZ, ZZ, sizeof(ZZ)));
-    CU(cudaMemcpyToSymbol(c_IZ, IZ, sizeof(IZ)));
     {
         uint2 izcol[8], izrow[8];
         for (int r = 0; r < 8; r++) {
