@@ -291,7 +291,7 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     for (int t = 0; t < gop_len; t++) {
         Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
         const int per = TR_THREADS / 8;
-        dim3 lgrid((4 * g.nmb + per - 1) / per, G), cgrid((2 * g.nmb + per - 1) / per, G);
+        dim3 lgrid((g.nmb + per - 1) / per, G), cgrid(lgrid);   // one 8-lane group per macroblock
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_ENC, s);
             intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
@@ -315,7 +315,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     for (int t = 0; t < gop_len; t++) {
         Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
         const int per = TR_THREADS / 8;
-        dim3 lgrid((4 * g.nmb + per - 1) / per, G), cgrid((2 * g.nmb + per - 1) / per, G);
+        dim3 lgrid((g.nmb + per - 1) / per, G), cgrid(lgrid);   // one 8-lane group per macroblock
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_DEC, s);
             intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
