@@ -455,7 +455,16 @@ def main():
             return
         print(json.dumps(reference_arm(args)), flush=True)
         return
-    line = ours(args)
+    # stdout carries exactly ONE JSON line: anything libraries print meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     if line is not None:
         print(json.dumps(line), flush=True)
 
