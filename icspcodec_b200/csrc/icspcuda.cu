@@ -826,10 +826,38 @@ int icsp_decode_gops(icsp_ctx* c, const icsp_dec_in* in, int n_gops, int gop_len
 {
     int rc = check_run(c, n_gops, gop_len, qdc, qac);
     if (rc) return rc;
-    const int n = n_gops * gop_len;
-    if ((rc = icsp_dec_upload(c, in, n))) return rc;
-    if ((rc = icsp_dec_run(c, n_gops, gop_len, qdc, qac))) return rc;
-    if ((rc = icsp_dec_download(c, n, out))) return rc;
+    if (!in || !in->levels || !in->mpm || !in->ipm || !in->mvd || !out) return fail(c, ICSP_ERR_PARAM, "icsp_decode_gops: bad arguments");
+    CU(cudaSetDevice(c->device));
+    const Geom& g = c->g;
+    const size_t nmb = (size_t)g.nmb;
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->s_up, c->ev_fork, 0));
+    for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
+    CU(cudaStreamWaitEvent(c->s_down, c->ev_fork, 0));
+    // software pipeline over GOP chunks: H2D of the parsed syntax | reconstruction kernels | D2H of the decoded frames
+    const int cg = chunk_gops(c, n_gops, true);
+    for (int g0 = 0, i = 0; g0 < n_gops; g0 += cg, i++) {
+        const int G = std::min(cg, n_gops - g0);
+        const size_t f0 = (size_t)g0 * gop_len, cnt = (size_t)G * gop_len;
+        cudaStream_t cs = c->cstream[i % c->n_cstreams];
+        CU(cudaMemcpyAsync(c->d_levels + f0 * nmb * 384, in->levels + f0 * nmb * 384, cnt * nmb * 384 * 2, cudaMemcpyHostToDevice, c->s_up));
+        CU(cudaMemcpyAsync(c->d_mpm + f0 * nmb * 4, in->mpm + f0 * nmb * 4, cnt * nmb * 4, cudaMemcpyHostToDevice, c->s_up));
+        CU(cudaMemcpyAsync(c->d_ipm + f0 * nmb * 4, in->ipm + f0 * nmb * 4, cnt * nmb * 4, cudaMemcpyHostToDevice, c->s_up));
+        CU(cudaMemcpyAsync(c->d_mvd + f0 * nmb * 2, in->mvd + f0 * nmb * 2, cnt * nmb * 4, cudaMemcpyHostToDevice, c->s_up));
+        cudaEvent_t up = chunk_event(c, 3 * i), done = chunk_event(c, 3 * i + 1);
+        CU(cudaEventRecord(up, c->s_up));
+        CU(cudaStreamWaitEvent(cs, up, 0));
+        if ((rc = decode_chunk(c, g0, G, gop_len, qdc, qac, cs))) return rc;
+        CU(cudaEventRecord(done, cs));
+        CU(cudaStreamWaitEvent(c->s_down, done, 0));
+        CU(cudaMemcpyAsync(out + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, c->s_down));
+    }
+    if ((rc = join_streams(c))) return rc;
+    CU(cudaEventRecord(c->ev_join[0], c->s_down));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+    CU(cudaEventRecord(c->ev_join[1], c->s_up));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+    CU(cudaGetLastError());
     return icsp_sync(c);
 }
 
