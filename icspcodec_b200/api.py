@@ -212,7 +212,8 @@ class IcspCuda:
         return stream_header(self.w, self.h, qp_dc, qp_ac, intra_period) + bytes(body), (np.concatenate(recs) if want_recon else None)
 
     # ---- decoder -----------------------------------------------------------------------------------
-    def decode_gops(self, levels, mpm, ipm, mvd, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int) -> np.ndarray:
+    def decode_gops(self, levels, mpm, ipm, mvd, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int,
+                    out: np.ndarray | None = None) -> np.ndarray:
         n = n_gops * gop_len
         levels = np.ascontiguousarray(levels, np.int16)
         mpm = np.ascontiguousarray(mpm, np.uint8)
@@ -220,7 +221,8 @@ class IcspCuda:
         mvd = np.ascontiguousarray(mvd, np.int16)
         assert levels.size == n * self.nmb * 384
         din = _lib.DecIn(_ptr(levels), _ptr(mpm), _ptr(ipm), _ptr(mvd))
-        out = np.zeros((n, self.fb), np.uint8)
+        if out is None:
+            out = np.zeros((n, self.fb), np.uint8)
         self._chk(self.lib.icsp_decode_gops(self.h_ctx, C.byref(din), n_gops, gop_len, qp_dc, qp_ac, _ptr(out)), "icsp_decode_gops")
         return out
 

@@ -405,6 +405,9 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
         for (int by0 = by_lo; by0 <= by_hi; by0 += ngrp) {  // whole warps iterate together
             const int by = by0 + grp;
             const bool active = by <= by_hi;
+            // a warp holds 4 block slots: when none of them has a block in this wave the whole warp skips the body
+            // (warp-uniform, so the __syncwarp / shuffles inside stay converged) and only meets the others at the barrier
+            if (by0 + (grp & ~3) > by_hi) continue;
             const int bx = active ? wv - 2 * by : 0, byy = active ? by : 0;
             const bool hasL = bx > 0, hasU = byy > 0;
             const int mb = (byy >> 1) * g.mbw + (bx >> 1), k = ((byy & 1) << 1) | (bx & 1);
