@@ -218,10 +218,10 @@ def workload_config(args) -> dict:
 # ---- our arm ------------------------------------------------------------------------------------------------
 ALG_BYTES = {  # algorithmic HBM bytes per frame each kernel must move (DESIGN.md "Kernels")
     "me_sad_kernel": 2 * W * H + NMB * 8,                                    # cur Y + ref Y + mv + minsad
-    "fdct_quant_kernel": 2 * W * H + NMB * 4 * (128 + 1 + 8),                # luma: cur + ref -> levels, acflag, raw DC
-    "fdct_quant_kernel<chroma>": W * H + NMB * 2 * (128 + 1 + 8),            # Cb + Cr (P frames; intra frames read no ref)
-    "idct_recon_kernel<enc>": NMB * 4 * (128 + 4) + 2 * W * H,               # luma: levels, DC + ref -> recon
-    "idct_recon_kernel<enc,chroma>": NMB * 2 * (128 + 4) + W * H,
+    "fdct_quant_kernel": 2 * FB + NMB * 6 * (128 + 1 + 8),                   # P frames: cur + ref -> levels, acflag, raw DC
+    "fdct_quant_kernel(intra: chroma only)": W * H // 2 + NMB * 2 * (128 + 1 + 8),   # I frames: Cb + Cr, no reference
+    "idct_recon_kernel<enc>": NMB * 6 * (128 + 4) + 2 * FB,                  # P frames: levels, DC + ref -> recon
+    "idct_recon_kernel<enc>(intra)": NMB * 2 * (128 + 4) + W * H // 2,
     "intra_luma_kernel<enc>": 2 * W * H + NMB * 4 * (128 + 3),               # cur Y -> recon Y, levels, flags
     "dc_chain_kernel": NMB * 6 * (8 + 4 + 2) + NMB * 8,
     "entropy_size_kernel": NMB * 6 * (128 + 1 + 4),                          # levels + acflag -> block bit lengths
@@ -370,7 +370,9 @@ def ours(args) -> dict | None:
         elif name.startswith("me_"):
             frames_k = p_frames
         elif name in ("fdct_quant_kernel", "idct_recon_kernel<enc>"):
-            frames_k = p_frames                       # luma launches exist on P frames only
+            frames_k = p_frames
+        elif name.endswith("(intra: chroma only)") or name.endswith("(intra)"):
+            frames_k = i_frames
         elif name.startswith("dc_chain"):
             frames_k = p_frames + i_frames / 3.0      # on intra frames the chain kernel walks the 2 chroma planes only
         else:

@@ -81,15 +81,30 @@ constexpr int TR_THREADS = 128;  // 16 blocks per CTA
 // Global memory + read-only path: a lane-indexed __constant__ table would serialise 8 ways.
 __device__ uint2 g_izcol[8], g_izrow[8];
 __device__ __forceinline__ int iz_byte(const uint2& t, int i) { return (int)(((i < 4 ? t.x : t.y) >> (8 * (i & 3))) & 255u); }
-// One 8-lane group owns a whole macroblock: its 4 luma blocks (CHROMA == false) or its Cb and Cr blocks (CHROMA == true)
-// are processed one after the other, so the macroblock-level work (coordinates, motion vector, base addresses) is paid
-// once, and the pixel loads of block k+1 are issued before the arithmetic of block k.
-template <bool CHROMA>
+// One 8-lane group owns a whole macroblock: its blocks k0..k1-1 (inter frames: Y0..Y3, Cb, Cr; intra frames: Cb, Cr
+// only) are processed one after the other, so the macroblock-level work (coordinates, motion vector, base addresses)
+// is paid once, and the pixel loads of block k+1 are issued before the arithmetic of block k.  All groups of a warp are
+// at the same k, so the luma/chroma differences (plane geometry, pad, mv/2, quantiser rounding) are warp-uniform.
+struct MbBlock { int poff, bx, by, pw, ph, pad, mx, my, dcidx; };
+__device__ __forceinline__ MbBlock mb_block(const Geom& g, int mb, int mbx, int mby, int k, int mx, int my)
+{
+    MbBlock b;
+    if (k < 4) {
+        b.poff = 0; b.bx = 2 * mbx + (k & 1); b.by = 2 * mby + (k >> 1); b.pw = g.w; b.ph = g.h; b.pad = 16;
+        b.mx = mx; b.my = my;                               // motionCompensation ENC:2185-2186
+        b.dcidx = b.by * g.bw + b.bx;
+    } else {
+        b.poff = g.w * g.h + (k - 4) * g.cw * g.ch; b.bx = mbx; b.by = mby; b.pw = g.cw; b.ph = g.ch; b.pad = 8;
+        b.mx = mx / 2; b.my = my / 2;                       // CmotionCompensation ENC:2538-2539: truncation toward zero
+        b.dcidx = 4 * g.nmb + (k - 4) * g.nmb + mb;
+    }
+    return b;
+}
+
 __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
     __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][72];   // 144-byte rows: the 4 groups of a warp land on different banks
-    constexpr int NB = CHROMA ? 2 : 4;
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
     const int mbi = blockIdx.x * (TR_THREADS / 8) + grp;
     const bool valid = mbi < g.nmb;
@@ -105,49 +120,53 @@ __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtr
     if (!st.intra) {
         const int mvw = *(const int*)(p.mv + (f * g.nmb + mb) * 2);
         mx = (int)(int16_t)(mvw & 0xffff); my = mvw >> 16;
-        if (CHROMA) { mx /= 2; my /= 2; }                  // CmotionCompensation ENC:2538-2539: truncation toward zero
     }
-    const int pw = CHROMA ? g.cw : g.w, ph = CHROMA ? g.ch : g.h, pad = CHROMA ? 8 : 16;
-    // block k of the macroblock: plane offset and position (luma: 2x2 blocks; chroma: same position in Cb and Cr)
+    const int k0 = st.intra ? 4 : 0;
     auto fetch = [&](int k, uint2& cw, uint2& pr) {
-        const int poff = CHROMA ? g.w * g.h + k * g.cw * g.ch : 0;
-        const int bx = CHROMA ? mbx : 2 * mbx + (k & 1), by = CHROMA ? mby : 2 * mby + (k >> 1);
-        cw = __ldg((const uint2*)(curf + poff + (unsigned)((by * 8 + r) * pw + bx * 8)));
+        const MbBlock b = mb_block(g, mb, mbx, mby, k, mx, my);
+        cw = __ldg((const uint2*)(curf + b.poff + (unsigned)((b.by * 8 + r) * b.pw + b.bx * 8)));
         pr = make_uint2(0u, 0u);
-        if (!st.intra) pr = ref_row8_packed(prevf + poff, pw, ph, pad, pad + by * 8 + r - my, pad + bx * 8 - mx);
+        if (!st.intra) pr = ref_row8_packed(prevf + b.poff, b.pw, b.ph, b.pad, b.pad + b.by * 8 + r - b.my, b.pad + b.bx * 8 - b.mx);
     };
     uint2 cw, pr;
-    fetch(0, cw, pr);
+    fetch(k0, cw, pr);
     int16_t* lvmb = p.levels + (f * g.nmb + mb) * 384;
 #pragma unroll 1
-    for (int k = 0; k < NB; k++) {
+    for (int k = k0; k < 6; k++) {
         int e[8];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             e[i] = (int)((cw.x >> (8 * i)) & 255u) - (int)((pr.x >> (8 * i)) & 255u);
             e[4 + i] = (int)((cw.y >> (8 * i)) & 255u) - (int)((pr.y >> (8 * i)) & 255u);
         }
-        if (k + 1 < NB) fetch(k + 1, cw, pr);              // next block's pixels are in flight during this block's math
+        if (k + 1 < 6) fetch(k + 1, cw, pr);               // next block's pixels are in flight during this block's math
         double t[8], D[8];
         fdct_row(e, t, M);
         group_transpose(t, s_tile[grp], r);   // lane r now holds column u=r: t[y][r]
         fdct_col(t, r, D, M);                  // D[v][u=r]
         int nz = 0;
+        if (k < 4) {                           // warp-uniform: luma truncates (ENC:2780), chroma floors (ENC:4642)
 #pragma unroll
-        for (int v = 0; v < 8; v++) {
-            const int L = quant_magic(D[v], st.magic_ac, CHROMA);   // the DC slot (v == 0, r == 0) is rewritten by the DC chain kernel
-            s_lv[grp][iz_byte(izc, v)] = (int16_t)L;
-            if (!(v == 0 && r == 0)) nz |= L;
+            for (int v = 0; v < 8; v++) {
+                const int L = quant_magic(D[v], st.magic_ac, false);   // the DC slot (v == 0, r == 0) is rewritten by the DC chain kernel
+                s_lv[grp][iz_byte(izc, v)] = (int16_t)L;
+                if (!(v == 0 && r == 0)) nz |= L;
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                const int L = quant_magic(D[v], st.magic_ac, true);
+                s_lv[grp][iz_byte(izc, v)] = (int16_t)L;
+                if (!(v == 0 && r == 0)) nz |= L;
+            }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, nz != 0);
         __syncwarp();
         if (valid) {
-            const int kk = CHROMA ? 4 + k : k;
-            *(uint4*)(lvmb + kk * 64 + 8 * r) = *(const uint4*)(&s_lv[grp][8 * r]);
+            *(uint4*)(lvmb + k * 64 + 8 * r) = *(const uint4*)(&s_lv[grp][8 * r]);
             if (r == 0) {
-                p.acflag[(f * g.nmb + mb) * 6 + kk] = ((bal >> (8 * (grp & 3))) & 0xffu) ? 0 : 1;
-                const int dcidx = CHROMA ? 4 * g.nmb + k * g.nmb + mb : (2 * mby + (k >> 1)) * g.bw + 2 * mbx + (k & 1);
-                p.dcraw[(size_t)gop * 6 * g.nmb + dcidx] = D[0];
+                p.acflag[(f * g.nmb + mb) * 6 + k] = ((bal >> (8 * (grp & 3))) & 0xffu) ? 0 : 1;
+                p.dcraw[(size_t)gop * 6 * g.nmb + mb_block(g, mb, mbx, mby, k, 0, 0).dcidx] = D[0];
             }
         }
         __syncwarp();                          // s_lv is rewritten by the next block
@@ -270,13 +289,12 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step
 // Kernel C: dequantisation + IDCT + reconstruction (R9, R10, R13).  8 lanes per block.
 // TAB 0: encoder table (float widened) ; TAB 1: decoder table (binary64).
 // =====================================================================================================
-template <int TAB, bool CHROMA>
+template <int TAB>
 __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
     __shared__ __align__(16) int16_t s_lv[TR_THREADS / 8][72];   // 144-byte rows: the 4 groups of a warp land on different banks
     __shared__ __align__(8) uint8_t s_px[TR_THREADS / 8][72];
-    constexpr int NB = CHROMA ? 2 : 4;
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
     const int mbi = blockIdx.x * (TR_THREADS / 8) + grp;
     const bool valid = mbi < g.nmb;
@@ -292,30 +310,27 @@ __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtr
     if (!st.intra) {
         const int mvw = *(const int*)(p.mv + (f * g.nmb + mb) * 2);
         mx = (int)(int16_t)(mvw & 0xffff); my = mvw >> 16;
-        if (CHROMA) { mx /= 2; my /= 2; }
     }
-    const int pw = CHROMA ? g.cw : g.w, ph = CHROMA ? g.ch : g.h, pad = CHROMA ? 8 : 16;
     const int16_t* lvmb = p.levels + (f * g.nmb + mb) * 384;
     const int32_t* dcrec = p.dcrec + (size_t)gop * 6 * g.nmb;
+    const int k0 = st.intra ? 4 : 0;
     auto fetch = [&](int k, uint4& lv, uint2& pr, int& dc) {
-        const int kk = CHROMA ? 4 + k : k;
-        const int poff = CHROMA ? g.w * g.h + k * g.cw * g.ch : 0;
-        const int bx = CHROMA ? mbx : 2 * mbx + (k & 1), by = CHROMA ? mby : 2 * mby + (k >> 1);
-        lv = __ldg((const uint4*)(lvmb + kk * 64 + 8 * r));
+        const MbBlock b = mb_block(g, mb, mbx, mby, k, mx, my);
+        lv = __ldg((const uint4*)(lvmb + k * 64 + 8 * r));
         pr = make_uint2(0u, 0u);
-        if (!st.intra) pr = ref_row8_packed(prevf + poff, pw, ph, pad, pad + by * 8 + r - my, pad + bx * 8 - mx);
+        if (!st.intra) pr = ref_row8_packed(prevf + b.poff, b.pw, b.ph, b.pad, b.pad + b.by * 8 + r - b.my, b.pad + b.bx * 8 - b.mx);
         dc = 0;
-        if (r == 0) dc = dcrec[CHROMA ? 4 * g.nmb + k * g.nmb + mb : by * g.bw + bx];   // level*QstepDC + P from the DC chain
+        if (r == 0) dc = dcrec[b.dcidx];                   // level*QstepDC + P from the DC chain
     };
     uint4 lv; uint2 pr; int dc;
-    fetch(0, lv, pr, dc);
+    fetch(k0, lv, pr, dc);
 #pragma unroll 1
-    for (int k = 0; k < NB; k++) {
+    for (int k = k0; k < 6; k++) {
         *(uint4*)(&s_lv[grp][8 * r]) = lv;
         *(uint2*)(&s_px[grp][8 * r]) = pr;
         const int dck = dc;
         __syncwarp();
-        if (k + 1 < NB) fetch(k + 1, lv, pr, dc);          // next block's loads are in flight during this block's math
+        if (k + 1 < 6) fetch(k + 1, lv, pr, dc);           // next block's loads are in flight during this block's math
         int q[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][iz_byte(izr, u)] * st.qac;   // IQuantization_block
@@ -325,28 +340,28 @@ __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtr
         group_transpose(t, s_tile[grp], r);   // lane r holds column x=r: t[v][r]
         idct_col<TAB>(t, R, M);               // R[y][x=r]
         uint8_t out[8];
+        if (k < 4) {                             // warp-uniform
 #pragma unroll
-        for (int y = 0; y < 8; y++) {
-            const int pv = s_px[grp][y * 8 + r];
-            int v;
-            if (CHROMA && st.intra) {            // chroma intra, intraImgReconstruct ENC:1964-1971
-                v = (R[y] > 255.0) ? 255 : __double2int_rz(R[y]);
-                v = max(v, 0);
-            } else if (!CHROMA) {                // mergeBlock ENC:4812 truncates first, interYReconstruct ENC:2343-2346
-                v = clip255(pv + __double2int_rz(R[y]));
-            } else {                             // interCbCrReconstruct ENC:2605-2607 truncates the double sum
-                v = clip255(__double2int_rz(__dadd_rn((double)pv, R[y])));
+            for (int y = 0; y < 8; y++)          // mergeBlock ENC:4812 truncates first, interYReconstruct ENC:2343-2346
+                out[y] = (uint8_t)clip255((int)s_px[grp][y * 8 + r] + __double2int_rz(R[y]));
+        } else if (st.intra) {
+#pragma unroll
+            for (int y = 0; y < 8; y++) {        // chroma intra, intraImgReconstruct ENC:1964-1971
+                const int v = (R[y] > 255.0) ? 255 : __double2int_rz(R[y]);
+                out[y] = (uint8_t)max(v, 0);
             }
-            out[y] = (uint8_t)v;
+        } else {
+#pragma unroll
+            for (int y = 0; y < 8; y++)          // interCbCrReconstruct ENC:2605-2607 truncates the double sum
+                out[y] = (uint8_t)clip255(__double2int_rz(__dadd_rn((double)s_px[grp][y * 8 + r], R[y])));
         }
         __syncwarp();
 #pragma unroll
         for (int y = 0; y < 8; y++) s_px[grp][y * 8 + r] = out[y];
         __syncwarp();
         if (valid) {
-            const int poff = CHROMA ? g.w * g.h + k * g.cw * g.ch : 0;
-            const int bx = CHROMA ? mbx : 2 * mbx + (k & 1), by = CHROMA ? mby : 2 * mby + (k >> 1);
-            *(uint2*)(recf + poff + (unsigned)((by * 8 + r) * pw + bx * 8)) = *(const uint2*)(&s_px[grp][8 * r]);
+            const MbBlock b = mb_block(g, mb, mbx, mby, k, 0, 0);
+            *(uint2*)(recf + b.poff + (unsigned)((b.by * 8 + r) * b.pw + b.bx * 8)) = *(const uint2*)(&s_px[grp][8 * r]);
         }
         __syncwarp();                          // s_lv / s_px are rewritten by the next block
     }

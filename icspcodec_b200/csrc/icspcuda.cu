@@ -29,8 +29,8 @@ const char* const kKernelNames[K_COUNT] = {
     "intra_luma_kernel<enc>", "intra_luma_kernel<dec>", "fdct_quant_kernel", "dc_chain_kernel", "idct_recon_kernel<enc>",
     "idct_recon_kernel<dec>", "me_sad_kernel", "me_zero_kernel", "me_chain_kernel", "me_sad_kernel(fixup)",
     "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel", "entropy_size_kernel", "entropy_frame_scan_kernel",
-    "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel", "fdct_quant_kernel<chroma>",
-    "idct_recon_kernel<enc,chroma>", "idct_recon_kernel<dec,chroma>"};
+    "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel", "fdct_quant_kernel(intra: chroma only)",
+    "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)"};
 
 struct Pending { int k; cudaEvent_t a, b; };
 
@@ -291,7 +291,7 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     for (int t = 0; t < gop_len; t++) {
         Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
         const int per = TR_THREADS / 8;
-        dim3 lgrid((g.nmb + per - 1) / per, G), cgrid(lgrid);   // one 8-lane group per macroblock
+        dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_ENC, s);
             intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
@@ -299,11 +299,9 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             const int rc = launch_me(c, p, st, G, s);
             if (rc) return rc;
         }
-        if (!st.intra) { LaunchScope ls(c, K_FDCT, s); fdct_quant_kernel<false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_FDCT_C, s); fdct_quant_kernel<true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, st.intra ? K_FDCT_C : K_FDCT, s); fdct_quant_kernel<<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
         { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 0, c->chain_staged); }
-        if (!st.intra) { LaunchScope ls(c, K_IDCT_ENC, s); idct_recon_kernel<0, false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_IDCT_ENC_C, s); idct_recon_kernel<0, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, st.intra ? K_IDCT_ENC_C : K_IDCT_ENC, s); idct_recon_kernel<0><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
 }
@@ -315,7 +313,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     for (int t = 0; t < gop_len; t++) {
         Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
         const int per = TR_THREADS / 8;
-        dim3 lgrid((g.nmb + per - 1) / per, G), cgrid(lgrid);   // one 8-lane group per macroblock
+        dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
         if (st.intra) {
             LaunchScope ls(c, K_INTRA_DEC, s);
             intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
@@ -324,8 +322,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             mv_recon_kernel<<<G, 32, 0, s>>>(g, p, st);
         }
         { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 1, c->chain_staged); }
-        if (!st.intra) { LaunchScope ls(c, K_IDCT_DEC, s); idct_recon_kernel<1, false><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_IDCT_DEC_C, s); idct_recon_kernel<1, true><<<cgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        { LaunchScope ls(c, st.intra ? K_IDCT_DEC_C : K_IDCT_DEC, s); idct_recon_kernel<1><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
 }
