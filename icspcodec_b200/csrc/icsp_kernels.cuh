@@ -778,8 +778,9 @@ __device__ __forceinline__ void me_task_store(const MeLayout& L, uint32_t* s_win
 
 // CPITCH / CSEG: compile-time copies of L.pitch_w / L.seg_mbs (0 = use the runtime values).  With constants every
 // shared-memory address of the inner loop is base + immediate, which removes the per-row pointer arithmetic.
+// (704, 1): one CTA per SM by shared memory anyway, so let the compiler use up to 93 registers to keep more loads in flight
 template <int CPITCH, int CSEG>
-__global__ void __launch_bounds__(704) me_sad_frame_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
+__global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
 {
     extern __shared__ __align__(16) unsigned char s_me[];
     const int pitch_w = CPITCH ? CPITCH : L.pitch_w, seg_mbs = CSEG ? CSEG : L.seg_mbs;
