@@ -186,3 +186,58 @@ def test_gpu_bitstream_stream_batch(gpu, oracle):
     assert np.array_equal(sbits, sbits2)
     for a, b in zip(bodies, bodies2):
         assert np.array_equal(a, b)
+
+
+def test_multi_chunk_pipelines_match(oracle):
+    """Force many small GOP chunks / several compute streams: the chunked, pipelined code paths (H2D | kernels | D2H,
+    per-chunk entropy regions and tables) must give exactly the results of the single-chunk run."""
+    from icspcodec_b200 import IcspCuda
+    clips = [synth.make_clip("highmotion", 6, 900 + i) for i in range(3)] + [synth.make_clip("flat", 6, 7), synth.make_clip("akiyo", 6, 5)]
+    frames = np.concatenate(clips, axis=0)
+    with IcspCuda(W, H, max_frames=32) as ctx:
+        ctx.configure(1, 0)
+        ref = ctx.encode_gops(frames, 10, 3, 8, 8)
+        rb, rbits, rrec = ctx.encode_streams(frames, 5, 2, 3, 8, 8, want_recon=True)
+        for nstreams, cg in ((3, 1), (4, 2), (2, 3)):
+            ctx.configure(nstreams, cg)
+            got = ctx.encode_gops(frames, 10, 3, 8, 8)
+            assert_syntax_equal(got, ref, what=f"streams={nstreams} chunk={cg}: ")
+            b, bits, rec = ctx.encode_streams(frames, 5, 2, 3, 8, 8, want_recon=True)
+            assert np.array_equal(bits, rbits) and np.array_equal(rec, rrec)
+            for x, y in zip(b, rb):
+                assert np.array_equal(x, y)
+            dec = ctx.decode_gops(ref.levels, ref.mpm, ref.ipm, ref.mvd, 10, 3, 8, 8)
+            s0 = oracle.encode(clips[0], W, H, 8, 8, 3)
+            assert np.array_equal(dec[:6], oracle.decode(s0, W, H, 8, 8, 3))
+
+
+@pytest.mark.parametrize("qdc,qac", [(3, 7), (100, 255), (1, 2), (16, 1)])
+def test_unusual_quantisers(gpu, oracle, qdc, qac):
+    """Any positive QP is accepted by the reference CLI (ENC:94-165); the magic-number division must stay exact."""
+    clip = synth.make_clip("highmotion", 4, 77)
+    res = gpu.encode_sequence(clip, qdc, qac, 4)
+    s = oracle.encode(clip, W, H, qdc, qac, 4)
+    assert_syntax_equal(res, s, what=f"q={qdc}/{qac}: ")
+    data, _ = gpu.encode_sequence_bitstream(clip, qdc, qac, 4)
+    assert data == oracle.write_bitstream(s, W, H, qdc, qac, 4)
+    out = gpu.decode_sequence(res.levels, res.mpm, res.ipm, res.mvd, qdc, qac, 4)
+    assert np.array_equal(out, oracle.decode(s, W, H, qdc, qac, 4))
+
+
+def test_extreme_content(gpu, oracle):
+    """Saturated / checkerboard / black frames: clipping paths, maximum residuals, all-zero blocks, zero-SAD everywhere."""
+    n = 4
+    y = np.zeros((n, H, W), np.uint8)
+    y[0] = 255
+    y[1, ::2, ::2] = 255; y[1, 1::2, 1::2] = 255
+    y[2] = 0
+    y[3] = (np.indices((H, W)).sum(0) % 256).astype(np.uint8)
+    c = np.zeros((n, 2, H // 2, W // 2), np.uint8)
+    c[0] = 255; c[1] = 0; c[2] = 128; c[3, 0] = 255; c[3, 1] = 1
+    frames = np.concatenate([y.reshape(n, -1), c.reshape(n, -1)], axis=1)
+    for q, ip in ((1, 4), (8, 2), (16, 1)):
+        res = gpu.encode_sequence(frames, q, q, ip)
+        s = oracle.encode(frames, W, H, q, q, ip)
+        assert_syntax_equal(res, s, what=f"extreme q={q} ip={ip}: ")
+        out = gpu.decode_sequence(res.levels, res.mpm, res.ipm, res.mvd, q, q, ip)
+        assert np.array_equal(out, oracle.decode(s, W, H, q, q, ip))
