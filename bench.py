@@ -216,6 +216,9 @@ def workload_config(args) -> dict:
 
 
 # ---- our arm ------------------------------------------------------------------------------------------------
+DP_OPS = {  # FP64 instructions per 8x8 block x 8 lanes (DMUL + DADD + DFMA in the SASS of one lane)
+    "fdct_quant_kernel": 8 * 158, "idct_recon_kernel<enc>": 8 * 146,
+}
 ALG_BYTES = {  # algorithmic HBM bytes per frame each kernel must move (DESIGN.md "Kernels")
     "me_sad_kernel": 2 * W * H + NMB * 8,                                    # cur Y + ref Y + mv + minsad
     "fdct_quant_kernel": 2 * FB + NMB * 6 * (128 + 1 + 8),                   # P frames: cur + ref -> levels, acflag, raw DC
@@ -360,6 +363,7 @@ def ours(args) -> dict | None:
     e2e_value = world * n * args.e2e_steps / (e2e_ms / 1e3)
     peak, peak_src = peaks()
     kernels = {}
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
     p_frames = n_gops * 9 * args.steps
     i_frames = n_gops * args.steps
     for name, s in stats.items():
@@ -385,6 +389,20 @@ def ours(args) -> dict | None:
             ent["hbm_frac"] = round(gbs / peak, 4)
         if name == "me_sad_kernel" and s["total_ms"] > 0:
             ent["Gpos_per_s"] = round(p_frames * NMB * 64 / (s["total_ms"] * 1e-3) / 1e9, 2)
+            # the resource that actually binds: every SAD word is one 4-byte shared-memory read (64 candidates x 256 B per MB,
+            # + 16 broadcast current rows), against 128 B/clk/SM at the sampled SM clock
+            smem_bytes = p_frames * NMB * (64 * 256 + 16 * 16 * 2)
+            peak_smem = 148 * 128 * sm_hz / 1e9
+            ent["binding"] = {"resource": "shared-memory bandwidth", "achieved_GBps": round(smem_bytes / (s["total_ms"] * 1e-3) / 1e9, 1),
+                              "peak_GBps": round(peak_smem, 1), "frac": round(smem_bytes / (s["total_ms"] * 1e-3) / 1e9 / peak_smem, 3)}
+        if name in DP_OPS and s["total_ms"] > 0:
+            # strict binary64 without FMA: FP64 lane-operations actually issued per 8x8 block (SASS count) against
+            # 64 DP lanes/clk/SM (measured: one warp-wide FP64 instruction per 2 cycles per SM sub-partition)
+            blocks = frames_k * NMB * (4 if name.startswith("intra_luma") else 6)
+            dp = blocks * DP_OPS[name]
+            peak_dp = 148 * 64 * sm_hz / 1e12
+            ent["binding"] = {"resource": "FP64 issue", "achieved_Tops": round(dp / (s["total_ms"] * 1e-3) / 1e12, 2),
+                              "peak_Tops": round(peak_dp, 2), "frac": round(dp / (s["total_ms"] * 1e-3) / 1e12 / peak_dp, 3)}
         kernels[name] = ent
     core = {k: v for k, v in kernels.items() if not k.startswith("entropy_")}
     dom = max(core, key=lambda k: core[k]["total_ms"])
