@@ -37,7 +37,7 @@ EXPORTS = [
     "icsp_set_profiling", "icsp_reset_stats", "icsp_get_stats", "icsp_launch_count",
     "icsp_event_record", "icsp_event_elapsed_ms",
     "icsp_host_alloc", "icsp_host_free",
-    "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body",
+    "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body", "icsp_bits_bound",
 ]
 
 _lib = None
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     lib.icsp_bits_download.argtypes = [vp, i, C.POINTER(BitsOut)]
     lib.icsp_finish_body.argtypes = [vp, C.c_uint64]
     lib.icsp_finish_body.restype = C.c_size_t
+    lib.icsp_bits_bound.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.icsp_bits_bound.restype = C.c_size_t
     lib.icsp_host_alloc.argtypes = [C.c_size_t]
     lib.icsp_host_alloc.restype = vp
     lib.icsp_host_free.argtypes = [vp]

@@ -168,7 +168,7 @@ class IcspCuda:
         n = n_streams * gops_per_stream * gop_len
         if frames.size != n * self.fb:
             raise IcspError(f"expected {n} frames of {self.fb} bytes")
-        cap = n * (self.w * self.h + 32) + 64
+        cap = self.lib.icsp_bits_bound(self.w, self.h, n)
         bits = bits_buf if bits_buf is not None else np.zeros(cap, np.uint8)
         sbits = np.zeros(n_streams, np.uint64)
         soff = np.zeros(n_streams, np.uint64)

@@ -329,6 +329,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
 
 // ---- entropy coding ------------------------------------------------------------------------------------
 constexpr int MAX_EN_CHUNKS = 64;
+static inline unsigned long long en_frame_cap(const Geom& g) { return (unsigned long long)g.nmb * 800 + 32; }
 int entropy_alloc(icsp_ctx* c)
 {
     if (c->d_bits) return ICSP_OK;
@@ -339,8 +340,10 @@ int entropy_alloc(icsp_ctx* c)
     CU(cudaMalloc(&c->d_streamoff, F * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->d_chunktotal, MAX_EN_CHUNKS * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->d_overflow, MAX_EN_CHUNKS * sizeof(uint32_t)));
-    // same bound as the reference's own buffer: width*height bytes per frame (ENC:4874-4875), + alignment slack
-    CU(cudaMalloc(&c->d_bits, F * (size_t)c->g.w * c->g.h + F * 32 + 64));
+    // The reference sizes its buffer as width*height bytes per frame (ENC:4874-4875) and overruns it on noise at QP 1;
+    // here the region holds the worst case: the DCT is orthonormal, so sum(level^2) <= 64*255^2 per block and
+    // sum(len) <= 64*log2(mean(level^2)+256) < 1040 bits = 130 B per block, 6 blocks + 45 header bits < 800 B per MB.
+    CU(cudaMalloc(&c->d_bits, F * en_frame_cap(c->g) + 64));
     CU(cudaHostAlloc(&c->h_tables, (2 * F + 2 * MAX_EN_CHUNKS) * sizeof(unsigned long long), cudaHostAllocDefault));
     return ICSP_OK;
 }
@@ -351,7 +354,7 @@ int entropy_chunk(icsp_ctx* c, int ci, int s0, int ns, int gops_per_stream, int 
     const Geom& g = c->g;
     const int fps = gops_per_stream * gop_len;
     const size_t f0 = (size_t)s0 * fps, nf = (size_t)ns * fps, nmb = (size_t)g.nmb;
-    const unsigned long long per_frame = (unsigned long long)g.w * g.h + 32;
+    const unsigned long long per_frame = en_frame_cap(g);
     icsp_ctx::EnChunk ch{s0, ns, f0, nf, f0 * per_frame, nf * per_frame};
     if ((int)c->en_chunks.size() <= ci) c->en_chunks.resize(ci + 1);
     c->en_chunks[ci] = ch;
@@ -642,6 +645,12 @@ int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len
 }
 
 // ---- encoder + GPU entropy coding ------------------------------------------------------------------------
+size_t icsp_bits_bound(int width, int height, int n_frames)
+{
+    if (width <= 0 || height <= 0 || n_frames <= 0) return 0;
+    return (size_t)n_frames * ((size_t)(width / 16) * (height / 16) * 800 + 32) + 64;
+}
+
 size_t icsp_finish_body(uint8_t* body, uint64_t nbits)
 {
     const size_t full = (size_t)(nbits / 8);
@@ -701,7 +710,7 @@ static int body_to_host(icsp_ctx* c, int ci, const icsp_bits_out* out, size_t& d
 {
     const auto& ch = c->en_chunks[ci];
     const size_t F = (size_t)c->cap;
-    if (((uint32_t*)(c->h_tables + 2 * F + MAX_EN_CHUNKS))[ci]) return fail(c, ICSP_ERR_CAPACITY, "bitstream larger than width*height bytes per frame");
+    if (((uint32_t*)(c->h_tables + 2 * F + MAX_EN_CHUNKS))[ci]) return fail(c, ICSP_ERR_CAPACITY, "bitstream larger than the 800 bytes per macroblock worst case (corrupt levels?)");
     const size_t total = (size_t)c->h_tables[2 * F + ci];
     if (dst_off + total > out->cap_bytes) return fail(c, ICSP_ERR_CAPACITY, "icsp_bits_out.cap_bytes too small (%zu needed so far)", dst_off + total);
     CU(cudaMemcpyAsync(out->bits + dst_off, c->d_bits + ch.region_off, total, cudaMemcpyDeviceToHost, s));

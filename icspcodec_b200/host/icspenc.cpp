@@ -144,7 +144,7 @@ int main(int argc, char** argv)
                                  mvd + f0 * nmb * 2, nullptr, nullptr, recon ? recon + f0 * fb : nullptr};
                 s.rc = icsp_encode_gops(ctx, frames + f0 * fb, ng, s.gop_len, o.qdc, o.qac, &out);
             } else {   // entropy coding + bit packing on the GPU: only bits (and the reconstruction) cross PCIe
-                const size_t cap = (size_t)ng * s.gop_len * ((size_t)o.width * o.height + 32) + 64;
+                const size_t cap = icsp_bits_bound(o.width, o.height, ng * s.gop_len);
                 std::vector<uint8_t> buf(cap);
                 uint64_t nbits = 0, off = 0;
                 icsp_bits_out bo{buf.data(), cap, &nbits, &off, recon ? recon + f0 * fb : nullptr};

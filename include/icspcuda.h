@@ -101,8 +101,9 @@ int icsp_enc_download(icsp_ctx* ctx, int n_frames, const icsp_enc_out* out);    
  *                 string the reference concatenates in makebitstream (ENC:4873-4895); icsp_finish_body() applies the
  *                 reference's file rule (bits/8+1 bytes, tail bits right-aligned in the last byte).
  *   recon         optional [n][fb]; NULL = not copied back.
- * Returns ICSP_ERR_CAPACITY if cap_bytes is too small (a safe bound is width*height bytes per frame, the size of the
- * reference's own buffer, ENC:4874). */
+ * Returns ICSP_ERR_CAPACITY if cap_bytes is too small.  icsp_bits_bound() is always enough (800 bytes per macroblock:
+ * the worst case of the VLC over an orthonormal 8x8 DCT of 8-bit residuals); the reference's own buffer, width*height
+ * bytes per frame (ENC:4874), is enough for natural content but is overrun by noise at QP 1. */
 typedef struct icsp_bits_out {
     uint8_t* bits;
     size_t cap_bytes;
@@ -119,6 +120,8 @@ int icsp_bits_download(icsp_ctx* ctx, int n_streams, const icsp_bits_out* out); 
 /* In place: turns an MSB-first body of nbits bits (buffer must hold nbits/8+1 bytes) into the reference's file body;
  * returns its length nbits/8+1. */
 size_t icsp_finish_body(uint8_t* body, uint64_t nbits);
+/* worst-case size in bytes of the packed bodies of n_frames frames (any content, any QP), incl. alignment slack */
+size_t icsp_bits_bound(int width, int height, int n_frames);
 
 /* ---- decoder: replaces intraPredictionDecode / interPredictionDecode (double cosine table) -------- */
 int icsp_decode_gops(icsp_ctx* ctx, const icsp_dec_in* in, int n_gops, int gop_len, int qp_dc, int qp_ac,

@@ -241,3 +241,67 @@ def test_extreme_content(gpu, oracle):
         assert_syntax_equal(res, s, what=f"extreme q={q} ip={ip}: ")
         out = gpu.decode_sequence(res.levels, res.mpm, res.ipm, res.mvd, q, q, ip)
         assert np.array_equal(out, oracle.decode(s, W, H, q, q, ip))
+
+
+def _fuzz_clip(rng, n, w, h):
+    """Random mixture of flat areas, copied/shifted patches (exact matches -> zero-SAD early breaks and carried spiral
+    state), noise and gradients, so that rare control paths are hit."""
+    y = np.zeros((n, h, w), np.uint8)
+    base = rng.integers(0, 256, size=(h, w)).astype(np.uint8)
+    if rng.random() < 0.5:
+        base[:, : w // 2] = rng.integers(0, 256)
+    if rng.random() < 0.5:
+        base[h // 2:, :] = rng.integers(0, 256)
+    for i in range(n):
+        mode = rng.integers(0, 4)
+        if i == 0 or mode == 0:
+            f = base.copy()
+        elif mode == 1:                                   # exact global shift of the previous frame
+            f = np.roll(y[i - 1], (int(rng.integers(-3, 4)), int(rng.integers(-3, 4))), axis=(0, 1))
+        elif mode == 2:                                   # previous frame + sparse noise
+            f = y[i - 1].copy()
+            m = rng.random((h, w)) < 0.02
+            f[m] = rng.integers(0, 256, size=int(m.sum()))
+        else:                                             # identical frame
+            f = y[i - 1].copy()
+        y[i] = f
+    cb = rng.integers(0, 256, size=(n, h // 2, w // 2)).astype(np.uint8) if rng.random() < 0.5 else np.full((n, h // 2, w // 2), 128, np.uint8)
+    cr = np.roll(cb, 1, axis=2)
+    return np.concatenate([y.reshape(n, -1), cb.reshape(n, -1), cr.reshape(n, -1)], axis=1)
+
+
+def test_fuzz_small_geometries(oracle):
+    """Seeded fuzzing on small frames (16x16 .. 96x64), many QP / intra-period combinations, encoder + GPU bitstream +
+    decoder against the oracle."""
+    from icspcodec_b200 import IcspCuda
+    rng = np.random.default_rng(20261017)
+    geoms = [(16, 16), (32, 16), (48, 32), (64, 64), (96, 64), (80, 48)]
+    for w, h in geoms:
+        with IcspCuda(w, h, max_frames=16) as ctx:
+            for trial in range(6):
+                n = int(rng.integers(2, 9))
+                ip = int(rng.choice([0, 1, 2, 3, 5, 8]))
+                qdc, qac = int(rng.choice([1, 2, 5, 8, 16, 31])), int(rng.choice([1, 3, 8, 16, 40]))
+                clip = _fuzz_clip(rng, n, w, h)
+                res = ctx.encode_sequence(clip, qdc, qac, ip)
+                s = oracle.encode(clip, w, h, qdc, qac, ip)
+                assert_syntax_equal(res, s, what=f"{w}x{h} n={n} ip={ip} q={qdc}/{qac}: ")
+                data, _ = ctx.encode_sequence_bitstream(clip, qdc, qac, ip)
+                assert data == oracle.write_bitstream(s, w, h, qdc, qac, ip), f"{w}x{h} bitstream"
+                if ip > 0:
+                    out = ctx.decode_sequence(res.levels, res.mpm, res.ipm, res.mvd, qdc, qac, ip)
+                    assert np.array_equal(out, oracle.decode(s, w, h, qdc, qac, ip))
+
+
+def test_fuzz_cif_early_breaks(gpu, oracle):
+    """CIF clips built from exact shifts / repeats: thousands of zero-SAD early breaks with the spiral state carried
+    across macroblocks (ENC:2094-2148), through the exact fallback kernels."""
+    rng = np.random.default_rng(7)
+    for trial in range(3):
+        clip = _fuzz_clip(rng, 6, W, H)
+        res = gpu.encode_sequence(clip, 8, 8, 6)
+        s = oracle.encode(clip, W, H, 8, 8, 6)
+        assert_syntax_equal(res, s, what=f"trial {trial}: ")
+        ys = clip[:, : W * H]
+        _, _, evals = oracle.me(ys[1], s.recon[0][: W * H], W, H)
+        assert evals <= 396 * 64
