@@ -37,7 +37,7 @@ EXPORTS = [
     "icsp_set_profiling", "icsp_reset_stats", "icsp_get_stats", "icsp_launch_count",
     "icsp_event_record", "icsp_event_elapsed_ms",
     "icsp_host_alloc", "icsp_host_free",
-    "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body", "icsp_bits_bound",
+    "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body", "icsp_bits_bound", "icsp_enc_sse",
 ]
 
 _lib = None
@@ -63,6 +63,7 @@ def load() -> C.CDLL:
     lib.icsp_enc_upload.argtypes = [vp, vp, i]
     lib.icsp_enc_run.argtypes = [vp, i, i, i, i]
     lib.icsp_enc_download.argtypes = [vp, i, C.POINTER(EncOut)]
+    lib.icsp_enc_sse.argtypes = [vp, i, vp]
     lib.icsp_decode_gops.argtypes = [vp, C.POINTER(DecIn), i, i, i, i, vp]
     lib.icsp_dec_upload.argtypes = [vp, C.POINTER(DecIn), i]
     lib.icsp_dec_run.argtypes = [vp, i, i, i, i]

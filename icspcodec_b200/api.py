@@ -160,6 +160,18 @@ class IcspCuda:
     def sync(self):
         self._chk(self.lib.icsp_sync(self.h_ctx), "icsp_sync")
 
+    def enc_sse(self, n: int) -> np.ndarray:
+        """[n][3] uint64 plane SSE (Y, Cb, Cr) of the resident frames against their reconstruction (§8 f4)."""
+        sse = np.zeros((n, 3), np.uint64)
+        self._chk(self.lib.icsp_enc_sse(self.h_ctx, n, _ptr(sse)), "icsp_enc_sse")
+        return sse
+
+    def psnr_y(self, n: int) -> float:
+        """Average luma PSNR as the reference decoder logs it (DEC.h:332-348)."""
+        mse = self.enc_sse(n)[:, 0].astype(np.float64) / float(self.w * self.h)
+        with np.errstate(divide="ignore"):
+            return float(np.mean(20.0 * np.log10(255.0 / np.sqrt(mse))))
+
     # ---- encoder with GPU entropy coding (SURVEY §8 f1) ------------------------------------------------
     def encode_streams(self, frames: np.ndarray, n_streams: int, gops_per_stream: int, gop_len: int, qp_dc: int, qp_ac: int,
                        want_recon: bool = False, bits_buf: np.ndarray | None = None, recon_buf: np.ndarray | None = None):

@@ -995,4 +995,37 @@ __global__ void __launch_bounds__(32) mv_recon_kernel(Geom g, FramePtrs p, Step 
     }
 }
 
+// ---- per-plane sum of squared errors between the source frames and the reconstruction (DEC.h:332-346 computes the luma
+// MSE in double; every term and partial sum is an integer < 2^53, so the integer sum is the same number).
+// grid (3 planes, frames), 256 threads; 16-byte loads, packed |a-b| then dp4a(d, d).  HBM-bound: 2 bytes read per pixel.
+__global__ void __launch_bounds__(256) plane_sse_kernel(Geom g, const uint8_t* __restrict__ cur, const uint8_t* __restrict__ rec,
+                                                        unsigned long long* __restrict__ sse)
+{
+    __shared__ unsigned long long s_part[8];
+    const int plane = blockIdx.x;
+    const size_t f = blockIdx.y;
+    const size_t ysz = (size_t)g.w * g.h, csz = ysz / 4;
+    const size_t off = f * g.fb + (plane == 0 ? 0 : plane == 1 ? ysz : ysz + csz);
+    const int n16 = (int)((plane == 0 ? ysz : csz) / 16);
+    const uint4* a = (const uint4*)(cur + off);
+    const uint4* b = (const uint4*)(rec + off);
+    unsigned long long acc = 0;
+    for (int i = threadIdx.x; i < n16; i += 256) {
+        const uint4 x = __ldg(a + i), y = __ldg(b + i);
+        const uint32_t d0 = __vabsdiffu4(x.x, y.x), d1 = __vabsdiffu4(x.y, y.y), d2 = __vabsdiffu4(x.z, y.z), d3 = __vabsdiffu4(x.w, y.w);
+        uint32_t t = __dp4a(d0, d0, 0u);
+        t = __dp4a(d1, d1, t); t = __dp4a(d2, d2, t); t = __dp4a(d3, d3, t);   // <= 16 * 255^2 per iteration
+        acc += t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; w++) t += s_part[w];
+        sse[f * 3 + plane] = t;
+    }
+}
+
 }  // namespace icsp

@@ -23,14 +23,14 @@ thread_local char g_create_error[256] = "";
 enum KernelId {
     K_INTRA_ENC = 0, K_INTRA_DEC, K_FDCT, K_DCCHAIN, K_IDCT_ENC, K_IDCT_DEC, K_ME_SAD, K_ME_ZERO, K_ME_CHAIN, K_ME_FIXUP,
     K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_EN_SIZE, K_EN_FSCAN, K_EN_SSCAN, K_EN_ZERO, K_EN_PACK, K_FDCT_C, K_IDCT_ENC_C,
-    K_IDCT_DEC_C, K_COUNT
+    K_IDCT_DEC_C, K_SSE, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "intra_luma_kernel<enc>", "intra_luma_kernel<dec>", "fdct_quant_kernel", "dc_chain_kernel", "idct_recon_kernel<enc>",
     "idct_recon_kernel<dec>", "me_sad_kernel", "me_zero_kernel", "me_chain_kernel", "me_sad_kernel(fixup)",
     "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel", "entropy_size_kernel", "entropy_frame_scan_kernel",
     "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel", "fdct_quant_kernel(intra: chroma only)",
-    "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)"};
+    "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)", "plane_sse_kernel"};
 
 struct Pending { int k; cudaEvent_t a, b; };
 
@@ -64,6 +64,7 @@ struct icsp_ctx {
     unsigned long long *d_framebits = nullptr, *d_streambits = nullptr, *d_streamoff = nullptr, *d_chunktotal = nullptr;
     uint32_t* d_overflow = nullptr;
     uint8_t* d_bits = nullptr;
+    unsigned long long* d_sse = nullptr;      // [cap][3] plane SSE (allocated on first use)
     unsigned long long* h_tables = nullptr;   // pinned: [cap] stream bits, [cap] stream offsets, [64] chunk totals, [64] overflow
     struct EnChunk { int s0, ns; size_t f0, nf; unsigned long long region_off, region_cap; };
     std::vector<EnChunk> en_chunks;
@@ -528,7 +529,7 @@ void icsp_destroy(icsp_ctx* c)
     for (auto& s : c->slots) if (s) cudaEventDestroy(s);
     void* bufs[] = {c->d_cur, c->d_rec, c->d_levels, c->d_acflag, c->d_mpm, c->d_ipm, c->d_mvd, c->d_mv, c->d_minsad, c->d_dcraw,
                     c->d_dcrec, c->d_mestate, c->d_memoves, c->d_meflag, c->d_mezero, c->d_shim, c->d_blkbits, c->d_framebits,
-                    c->d_streambits, c->d_streamoff, c->d_chunktotal, c->d_overflow, c->d_bits, c->d_intra_edges};
+                    c->d_streambits, c->d_streamoff, c->d_chunktotal, c->d_overflow, c->d_bits, c->d_intra_edges, c->d_sse};
     if (c->h_tables) cudaFreeHost(c->h_tables);
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -977,6 +978,19 @@ int icsp_configure(icsp_ctx* c, int n_compute_streams, int chunk_gops_)
     c->n_cstreams = n_compute_streams;
     c->chunk_gops_target = chunk_gops_;
     return ICSP_OK;
+}
+
+// ---- quality numbers without the reconstruction read-back ----------------------------------
+int icsp_enc_sse(icsp_ctx* c, int n, uint64_t* sse)
+{
+    if (!c || !sse || n <= 0) return fail(c, ICSP_ERR_PARAM, "icsp_enc_sse: bad arguments");
+    if (n > c->cap) return fail(c, ICSP_ERR_CAPACITY, "%d frames > capacity %d", n, c->cap);
+    CU(cudaSetDevice(c->device));
+    if (!c->d_sse) CU(cudaMalloc(&c->d_sse, (size_t)c->cap * 3 * sizeof(unsigned long long)));
+    { LaunchScope ls(c, K_SSE, c->stream); plane_sse_kernel<<<dim3(3, n), 256, 0, c->stream>>>(c->g, c->d_cur, c->d_rec, c->d_sse); }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sse, c->d_sse, (size_t)n * 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    return icsp_sync(c);
 }
 
 int icsp_event_record(icsp_ctx* c, int slot)

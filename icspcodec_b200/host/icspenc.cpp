@@ -3,13 +3,14 @@
 // core (intraPrediction / interPrediction) on the GPU through libicspcuda, then the host bitstream writer.
 //
 //   icspenc -i <name_cif.yuv> -n <frames> [-q Q | --qpdc D --qpac A] [--intraPeriod P] [-w W -h H]
-//           [--EnMultiThread T] [--gpus G] [--no-recon] [--quiet]
+//           [--EnMultiThread T] [--gpus G] [--no-recon] [--psnr] [--quiet]
 //
 // Outputs, like the reference: <prefix>_compCIF_<QDC>_<QAC>_<IP>.bin (prefix = input name up to the first '_',
 // encoder_main.cpp:10-17) and test_yuv.yuv (reconstruction, ENC:6376-6421).  Unlike the reference's
 // --EnMultiThread mode, the bitstream is always written and tail frames (n % intraPeriod) are encoded.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,7 @@ struct Options {
     int qdc = 0, qac = 0, ip = 0, threads = 0, gpus = 1;
     int width = 352, height = 288;  // encoder_main.cpp:20 hard-wires CIF; -w/-h are accepted here
     bool recon = true, quiet = false;
+    bool psnr = false;          // --psnr: luma PSNR of the reconstruction, reduced on the GPU (what the reference's decoder logs, DEC.h:332-350)
     bool host_entropy = false;  // --host-entropy: download the syntax arrays and entropy-code on the CPU (round-1 path)
 };
 
@@ -39,7 +41,7 @@ void help()
            "--qpdc : QP of DC\n--qpac : QP of AC\n--intraPeriod: period of intra frame(0: All intra)\n"
            "--EnMultiThread: host threads for the entropy coder (0 = all cores)\n"
            "--gpus: GPUs to shard the GOPs over (default 1)\n--no-recon: do not write test_yuv.yuv\n"
-           "--host-entropy: entropy-code on the CPU instead of the GPU\n--help : help message\n");
+           "--host-entropy: entropy-code on the CPU instead of the GPU\n--psnr: print the average luma PSNR (computed on the GPU; works with --no-recon)\n--help : help message\n");
 }
 
 bool is_number(const char* s) { return s && *s && strspn(s, "0123456789") == strlen(s); }
@@ -63,6 +65,7 @@ int parse(int argc, char** argv, Options& o)
         else if (a == "--gpus") { if (!val(o.gpus)) return -1; }
         else if (a == "--no-recon") o.recon = false;
         else if (a == "--host-entropy") o.host_entropy = true;
+        else if (a == "--psnr") o.psnr = true;
         else if (a == "--quiet") o.quiet = true;
         else if (a[0] == '-') { fprintf(stderr, "[ERROR] uncorrect parameters in parsing_command\n"); return -1; }
     }
@@ -75,6 +78,7 @@ struct Shard {          // one GPU's contiguous range of GOPs
     int rc = 0;
     std::string err;
     std::vector<std::pair<std::vector<uint8_t>, uint64_t>> bits;   // GPU entropy path: MSB-first bit strings, in order
+    std::vector<uint64_t> sse;  // --psnr: [frames][3]
 };
 }  // namespace
 
@@ -155,6 +159,11 @@ int main(int argc, char** argv)
                     s.bits.emplace_back(std::move(buf), nbits);
                 }
             }
+            if (!s.rc && o.psnr) {   // the frames and their reconstruction are still resident
+                const size_t at = s.sse.size();
+                s.sse.resize(at + (size_t)ng * s.gop_len * 3);
+                s.rc = icsp_enc_sse(ctx, ng * s.gop_len, s.sse.data() + at);
+            }
             if (s.rc) s.err = icsp_last_error(ctx);
         }
         (void)cnt;
@@ -202,6 +211,12 @@ int main(int argc, char** argv)
         if (!fr) { fprintf(stderr, "fail to open test_yuv.yuv\n"); return 1; }
         fwrite(recon, fb, n, fr);
         fclose(fr);
+    }
+    if (o.psnr) {   // mean over frames of 20*log10(255/sqrt(MSE_Y)), the reference decoder's figure (DEC.h:332-348)
+        double acc = 0;
+        for (auto& s : shards)
+            for (size_t f = 0; f * 3 < s.sse.size(); f++) acc += 20. * log10(255. / sqrt((double)s.sse[f * 3] / ((double)o.width * o.height)));
+        printf("PSNR: %.4lf QPDC: %d  QPAC: %d Period: %d\n", acc / n, o.qdc, o.qac, o.ip);
     }
     if (!o.quiet) {
         const double core = std::chrono::duration<double>(t1 - t0).count(), ent = std::chrono::duration<double>(t2 - t1).count();

@@ -91,6 +91,11 @@ int icsp_encode_gops(icsp_ctx* ctx, const uint8_t* i420_frames, int n_gops, int 
 int icsp_enc_upload(icsp_ctx* ctx, const uint8_t* i420_frames, int n_frames);                 /* async H2D */
 int icsp_enc_run(icsp_ctx* ctx, int n_gops, int gop_len, int qp_dc, int qp_ac);               /* async */
 int icsp_enc_download(icsp_ctx* ctx, int n_frames, const icsp_enc_out* out);                  /* async D2H */
+/* Quality numbers without reading the reconstruction back (replaces the MSE loop of DEC.h:332-346 and
+ * the need for checkResultFrames' dump, ENC:6376-6421, when only PSNR is wanted): sse[f*3 + {0,1,2}] = sum over the
+ * Y / Cb / Cr plane of (source - reconstruction)^2 for the resident frames f < n_frames.  Synchronous.
+ * PSNR_Y(f) = 20*log10(255/sqrt(sse[f*3]/(width*height))), exactly the reference's double arithmetic. */
+int icsp_enc_sse(icsp_ctx* ctx, int n_frames, uint64_t* sse);
 
 /* ---- encoder with entropy coding + bit packing on the GPU ------------------------- */
 /* Replaces intraPrediction/interPrediction AND intraBody/interBody + DC/AC/MVentropy (ENC:5032-6334) for a batch of

@@ -101,3 +101,26 @@ def test_live_reference_binaries(tmp_path, oracle):
     assert np.array_equal(np.fromfile(tmp_path / "test_yuv.yuv", np.uint8).reshape(8, -1), rrec)
     subprocess.run([DEC, "8", "live_compCIF_8_8_4.bin", "8", "8", "4", "--out", "d.yuv"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
     assert np.array_equal(np.fromfile(tmp_path / "d.yuv", np.uint8).reshape(8, -1), oracle.ref_decode(rbin, 8, 8, 8, 4))
+
+
+def test_icspenc_psnr_on_gpu(tmp_path):
+    """--psnr: the figure the reference's decoder logs (mean luma PSNR, DEC.h:332-350), reduced on the GPU
+    from the resident frames, also with --no-recon; checked against the same formula on the written reconstruction."""
+    case = CASES[0]
+    n, qdc, qac, ip = case["nframes"], case["qdc"], case["qac"], case["ip"]
+    clip = synth.make_clip(case["kind"], n, case["seed"])
+    clip.tofile(tmp_path / "clip_cif.yuv")
+    r = subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", str(ip), "--psnr", "--quiet"],
+                       cwd=tmp_path, check=True, capture_output=True, text=True)
+    assert md5f(tmp_path / "test_yuv.yuv") == case["recon_md5"]
+    rec = np.fromfile(tmp_path / "test_yuv.yuv", np.uint8).reshape(n, -1)[:, : 352 * 288].astype(np.float64)
+    src = clip.reshape(n, -1)[:, : 352 * 288].astype(np.float64)
+    mse = ((src - rec) ** 2).sum(axis=1) / (352 * 288)
+    want = float(np.mean(20.0 * np.log10(255.0 / np.sqrt(mse))))
+    line = [l for l in r.stdout.splitlines() if l.startswith("PSNR:")][0]
+    assert line == f"PSNR: {want:.4f} QPDC: {qdc}  QPAC: {qac} Period: {ip}"
+    os.remove(tmp_path / "test_yuv.yuv")
+    r2 = subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", str(ip), "--psnr", "--quiet", "--no-recon"],
+                        cwd=tmp_path, check=True, capture_output=True, text=True)
+    assert [l for l in r2.stdout.splitlines() if l.startswith("PSNR:")][0] == line
+    assert not (tmp_path / "test_yuv.yuv").exists()

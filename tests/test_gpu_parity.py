@@ -305,3 +305,20 @@ def test_fuzz_cif_early_breaks(gpu, oracle):
         ys = clip[:, : W * H]
         _, _, evals = oracle.me(ys[1], s.recon[0][: W * H], W, H)
         assert evals <= 396 * 64
+
+
+def test_plane_sse_matches_numpy(gpu):
+    """icsp_enc_sse (§8 f4): integer SSE per plane of the resident frames vs their reconstruction, all three planes,
+    plus psnr_y against the reference decoder's double formula (DEC.h:332-348)."""
+    clip = synth.make_clip("highmotion", 6, 11)
+    res = gpu.encode_sequence(clip, 16, 16, 3)
+    sse = gpu.enc_sse(6)
+    a, b = clip.reshape(6, -1).astype(np.int64), res.recon.reshape(6, -1).astype(np.int64)
+    d2 = (a - b) ** 2
+    ysz, csz = W * H, W * H // 4
+    want = np.stack([d2[:, :ysz].sum(1), d2[:, ysz: ysz + csz].sum(1), d2[:, ysz + csz:].sum(1)], axis=1)
+    assert np.array_equal(sse.astype(np.int64), want)
+    mse = want[:, 0].astype(np.float64) / (W * H)
+    assert gpu.psnr_y(6) == float(np.mean(20.0 * np.log10(255.0 / np.sqrt(mse))))
+    with pytest.raises(Exception):
+        gpu.enc_sse(10 ** 9)
