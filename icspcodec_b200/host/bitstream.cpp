@@ -1,5 +1,6 @@
 #include "bitstream.h"
 
+#include <cstring>
 #include <algorithm>
 #include <cstdlib>
 #include <stdexcept>
@@ -136,28 +137,45 @@ std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_
 // ---- reader ------------------------------------------------------------------------------------------
 namespace {
 struct BitReader {
+    // `p` must be readable for 8 bytes past the last whole byte of the stream (parse_stream pads its copy with zeros);
+    // bits at or after nbits read as 0, as in the reference's reader on its zero-initialised buffer.
     const uint8_t* p; uint64_t nbits, pos = 0;
-    int peek(uint64_t off) const { const uint64_t q = pos + off; return q < nbits ? (p[q >> 3] >> (7 - (q & 7))) & 1 : 0; }
-    int get() { const int v = peek(0); pos++; return v; }
+    // the next >= 57 bits, left aligned (bit 63 = the bit at pos)
+    uint64_t window() const
+    {
+        if (pos >= nbits) return 0;
+        uint64_t w;
+        memcpy(&w, p + (pos >> 3), 8);
+        return __builtin_bswap64(w) << (pos & 7);
+    }
+    int get() { const int v = (int)(window() >> 63); pos++; return v; }
     int vlc()
     {   // DCientropy (DEC:407-608) and its AC/MV twins: 3-bit category prefix, then unary extension from category 6 up
-        const int b0 = peek(0), b1 = peek(1), b2 = peek(2);
-        if (!b0 && !b1) { pos += 2; return 0; }
-        if (!b0 && b1 && !b2) { const int s = peek(3); pos += 4; return s ? 1 : -1; }
+        const uint64_t w = window();
+        const unsigned top3 = (unsigned)(w >> 61);
+        if (top3 < 2) { pos += 2; return 0; }                                   // "00"
+        if (top3 == 2) { pos += 4; return (w >> 60) & 1 ? 1 : -1; }             // "010" + sign
         int e, prefix;
-        if (!(b0 && b1 && b2)) { e = ((b0 << 2) | (b1 << 1) | b2) - 2; prefix = 3; }
+        if (top3 != 7) { e = (int)top3 - 2; prefix = 3; }
         else {
-            int ones = 3;
-            while (ones < 10 && peek(ones)) ones++;
+            const int ones = __builtin_clzll(~w);                               // >= 3
             if (ones >= 10) return 0;              // no category matches: the reference leaves len = 0, val = 0
             e = ones + 2; prefix = ones + 1;
         }
-        const int s = peek(prefix);
-        int t = 0;
-        for (int n = 0; n < e; n++) t = (t << 1) | peek(prefix + 1 + n);
+        // prefix + 1 + e <= 10 + 1 + 11 = 22 bits: inside the window
+        const int s = (int)((w >> (63 - prefix)) & 1);
+        const int t = (int)((w << (prefix + 1)) >> (64 - e));
         pos += prefix + 1 + e;
         const int v = (1 << e) + t;
         return s ? v : -v;
+    }
+    // number of leading "00" symbols (at most `limit` <= 28) at pos, consumed
+    int zero_run(int limit)
+    {
+        const uint64_t w = window() | ((1ull << (63 - 2 * limit)) );            // sentinel one after `limit` pairs
+        const int z = __builtin_clzll(w) >> 1;
+        pos += 2 * (uint64_t)z;
+        return z;
     }
 };
 }  // namespace
@@ -178,7 +196,9 @@ ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes)
     const int nmb = (ps.p.width / 16) * (ps.p.height / 16);
     const size_t N = (size_t)nframes * nmb;
     ps.levels.assign(N * 384, 0); ps.acflag.assign(N * 6, 0); ps.mpm.assign(N * 4, 0); ps.ipm.assign(N * 4, 0); ps.mvd.assign(N * 2, 0);
-    BitReader r{file.data() + 14, (uint64_t)(file.size() - 14) * 8};
+    std::vector<uint8_t> padded(file.size() - 14 + 16, 0);              // the reader loads 8 bytes at a time
+    memcpy(padded.data(), file.data() + 14, file.size() - 14);
+    BitReader r{padded.data(), (uint64_t)(file.size() - 14) * 8};
     for (int n = 0; n < nframes; n++) {
         const bool intra = ps.p.intra_period == 1 || n % ps.p.intra_period == 0;   // DEC:98, DEC:201
         for (int mb = 0; mb < nmb; mb++) {
@@ -195,7 +215,10 @@ ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes)
                 const int f = r.get();
                 ps.acflag[m * 6 + k] = (uint8_t)f;
                 if (f == 1) r.pos += 63;
-                else for (int q = 1; q < 64; q++) zz[q] = (int16_t)r.vlc();
+                else for (int q = 1; q < 64;) {
+                    q += r.zero_run(std::min(28, 64 - q));                      // levels are pre-zeroed: skip runs of "00"
+                    if (q < 64) zz[q++] = (int16_t)r.vlc();
+                }
             }
         }
     }
