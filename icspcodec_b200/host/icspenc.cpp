@@ -129,9 +129,9 @@ int main(int argc, char** argv)
     std::vector<Shard> shards;
     for (int d = 0; d < G; d++) {
         const int g0 = (int)((long long)full * d / G), g1 = (int)((long long)full * (d + 1) / G);
-        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, "", {}});
+        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, "", {}, {}});
     }
-    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}});
+    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}, {}});
     auto run_shard = [&](Shard& s) {
         const int cnt = s.n_gops * s.gop_len;
         int call_frames = 4096;                                    // bound device memory per call
