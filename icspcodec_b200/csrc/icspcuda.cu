@@ -45,6 +45,9 @@ struct icsp_ctx {
                                             // chunk overlap throughput-bound kernels of another)
     cudaStream_t s_up = nullptr, s_down = nullptr;   // H2D / D2H copy streams of the pipelined one-shot calls
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
+    cudaStream_t hstream[4] = {};           // high-priority companions of cstream[] for the latency-bound kernels
+    cudaEvent_t ev_hi[4][2] = {};
+    bool hi_prio = true;
     std::vector<cudaEvent_t> ev_chunk;      // per-chunk upload / compute-done events
     int n_cstreams = 4;
     int chunk_gops_target = 0;              // 0 = automatic
@@ -261,6 +264,27 @@ MeLayout me_layout(const Geom& g)
     return L;
 }
 
+// The DC chains and the intra wavefront are latency-bound: a few long-lived CTAs per frame, ~115 dependent waves, a few
+// percent of the issue slots.  On the chunk's own stream they would queue behind the resident CTAs of the other chunks'
+// throughput kernels (which fill the register file) and then run alone.  hi_begin/hi_end move one launch to the chunk's
+// high-priority companion stream (fork/join with events): its CTAs are dispatched as soon as slots free up and run
+// underneath the transform / ME kernels of the other chunks.
+cudaStream_t hi_begin(icsp_ctx* c, cudaStream_t s, int& idx)
+{
+    idx = -1;
+    if (!c->hi_prio) return s;
+    for (int i = 0; i < 4; i++) if (c->cstream[i] == s) idx = i;
+    if (idx < 0) return s;
+    if (cudaEventRecord(c->ev_hi[idx][0], s) != cudaSuccess || cudaStreamWaitEvent(c->hstream[idx], c->ev_hi[idx][0], 0) != cudaSuccess) { idx = -1; return s; }
+    return c->hstream[idx];
+}
+void hi_end(icsp_ctx* c, cudaStream_t s, int idx)
+{
+    if (idx < 0) return;
+    cudaEventRecord(c->ev_hi[idx][1], c->hstream[idx]);
+    cudaStreamWaitEvent(s, c->ev_hi[idx][1], 0);
+}
+
 // motion estimation of step t for every GOP: speculative state-0 search, then the exact carried-state fallback
 // (no-ops unless some search of the frame broke early)
 int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream_t s)
@@ -294,14 +318,22 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
         const int per = TR_THREADS / 8;
         dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
         if (st.intra) {
-            LaunchScope ls(c, K_INTRA_ENC, s);
-            intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
+            int hi;
+            cudaStream_t h = hi_begin(c, s, hi);
+            { LaunchScope ls(c, K_INTRA_ENC, h);
+              intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr); }
+            hi_end(c, s, hi);
         } else {
             const int rc = launch_me(c, p, st, G, s);
             if (rc) return rc;
         }
         { LaunchScope ls(c, st.intra ? K_FDCT_C : K_FDCT, s); fdct_quant_kernel<<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
-        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 0, c->chain_staged); }
+        {
+            int hi;
+            cudaStream_t h = hi_begin(c, s, hi);
+            { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 0, c->chain_staged); }
+            hi_end(c, s, hi);
+        }
         { LaunchScope ls(c, st.intra ? K_IDCT_ENC_C : K_IDCT_ENC, s); idct_recon_kernel<0><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
@@ -443,6 +475,15 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     if (const char* e = getenv("ICSP_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= 4) c->n_cstreams = v; }
     if (const char* e = getenv("ICSP_CHUNK_GOPS")) { const int v = atoi(e); if (v >= 1) c->chunk_gops_target = v; }
     for (int i = 0; i < 4; i++) CUB(cudaStreamCreateWithFlags(&c->cstream[i], cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;
+        CUB(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        for (int i = 0; i < 4; i++) {
+            CUB(cudaStreamCreateWithPriority(&c->hstream[i], cudaStreamNonBlocking, greatest));
+            for (auto& e : c->ev_hi[i]) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        if (const char* e = getenv("ICSP_HI_PRIO")) c->hi_prio = atoi(e) != 0;
+    }
     CUB(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -522,6 +563,8 @@ void icsp_destroy(icsp_ctx* c)
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
     for (auto& st : c->cstream) if (st) cudaStreamDestroy(st);
+    for (auto& st : c->hstream) if (st) cudaStreamDestroy(st);
+    for (auto& ee : c->ev_hi) for (auto& e : ee) if (e) cudaEventDestroy(e);
     if (c->s_up) cudaStreamDestroy(c->s_up);
     if (c->s_down) cudaStreamDestroy(c->s_down);
     for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
