@@ -19,6 +19,10 @@ class DecIn(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("levels", "mpm", "ipm", "mvd")]
 
 
+class DecBitsIn(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("bits", "stream_offset", "stream_bytes", "row_bit_offset")]
+
+
 class BitsOut(C.Structure):
     _fields_ = [("bits", C.c_void_p), ("cap_bytes", C.c_size_t), ("stream_bits", C.c_void_p), ("stream_offset", C.c_void_p),
                 ("recon", C.c_void_p)]
@@ -37,7 +41,7 @@ EXPORTS = [
     "icsp_set_profiling", "icsp_reset_stats", "icsp_get_stats", "icsp_launch_count",
     "icsp_event_record", "icsp_event_elapsed_ms",
     "icsp_host_alloc", "icsp_host_free",
-    "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body", "icsp_bits_bound", "icsp_enc_sse",
+    "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body", "icsp_bits_bound", "icsp_enc_sse", "icsp_bits_row_index", "icsp_decode_streams",
 ]
 
 _lib = None
@@ -64,6 +68,8 @@ def load() -> C.CDLL:
     lib.icsp_enc_run.argtypes = [vp, i, i, i, i]
     lib.icsp_enc_download.argtypes = [vp, i, C.POINTER(EncOut)]
     lib.icsp_enc_sse.argtypes = [vp, i, vp]
+    lib.icsp_bits_row_index.argtypes = [vp, i, vp]
+    lib.icsp_decode_streams.argtypes = [vp, C.POINTER(DecBitsIn), i, i, i, i, i, vp]
     lib.icsp_decode_gops.argtypes = [vp, C.POINTER(DecIn), i, i, i, i, vp]
     lib.icsp_dec_upload.argtypes = [vp, C.POINTER(DecIn), i]
     lib.icsp_dec_run.argtypes = [vp, i, i, i, i]

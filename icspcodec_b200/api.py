@@ -202,26 +202,55 @@ class IcspCuda:
         self._chk(self.lib.icsp_bits_download(self.h_ctx, n_streams, C.byref(o)), "icsp_bits_download")
         return [bits[int(soff[s]): int(soff[s]) + (int(sbits[s]) + 7) // 8] for s in range(n_streams)], sbits
 
-    def encode_sequence_bitstream(self, frames: np.ndarray, qp_dc: int, qp_ac: int, intra_period: int, want_recon: bool = False):
+    def encode_sequence_bitstream(self, frames: np.ndarray, qp_dc: int, qp_ac: int, intra_period: int, want_recon: bool = False,
+                                  want_index: bool = False):
         """One stream -> the complete reference-format file (header + body), entropy coded on the GPU.  Full GOPs and
-        the tail GOP are two device calls whose bit strings are concatenated here."""
+        the tail GOP are two device calls whose bit strings are concatenated here.  want_index: also return the
+        macroblock-row index [n][mbh] (bit offsets from the body start) that decode_sequence_bitstream consumes."""
         frames = np.ascontiguousarray(frames, np.uint8).reshape(-1, self.fb)
         n = frames.shape[0]
         ip = 1 if intra_period == 0 else intra_period
         full, tail = divmod(n, ip)
-        segs, recs = [], []
+        segs, recs, idx = [], [], []
         if full:
             b, sb, r = self.encode_streams(frames[: full * ip], 1, full, ip, qp_dc, qp_ac, want_recon)
             segs.append((b[0], int(sb[0]))); recs.append(r)
+            if want_index:
+                idx.append(self.bits_row_index(full * ip))
         if tail:
             b, sb, r = self.encode_streams(frames[full * ip:], 1, 1, tail, qp_dc, qp_ac, want_recon)
+            if want_index:
+                idx.append(self.bits_row_index(tail) + np.uint64(segs[0][1] if segs else 0))
             segs.append((b[0], int(sb[0]))); recs.append(r)
         bits = np.concatenate([np.unpackbits(b)[:nb] for b, nb in segs])
         nb = bits.size
         body = bytearray(np.packbits(bits).tobytes()) if nb % 8 else bytearray(np.packbits(bits).tobytes() + b"\x00")
         if nb % 8:
             body[-1] = body[-1] >> (8 - nb % 8)              # reference tail rule (ENC:4895): right-aligned last byte
-        return stream_header(self.w, self.h, qp_dc, qp_ac, intra_period) + bytes(body), (np.concatenate(recs) if want_recon else None)
+        data = stream_header(self.w, self.h, qp_dc, qp_ac, intra_period) + bytes(body)
+        if want_index:
+            return data, (np.concatenate(recs) if want_recon else None), np.concatenate(idx)
+        return data, (np.concatenate(recs) if want_recon else None)
+
+    def decode_sequence_bitstream(self, data: bytes, rows: np.ndarray, nframes: int) -> np.ndarray:
+        """A reference-format file + its macroblock-row index -> decoded frames, parsed on the GPU (§8 f3).  Header fields
+        as the reference decoder reads them (DEC:14-37); frame loop of IcspCodec::decoding (DEC.h:290-313)."""
+        if len(data) < 14:
+            raise IcspError("bitstream shorter than its 14-byte header")
+        qdc, qac = data[9], data[10]
+        ip = ((data[12] | (data[13] << 8)) & 0x1F80) >> 7
+        if ip < 1 or qdc == 0 or qac == 0:
+            raise IcspError("bad header (intraPeriod 0 / QP 0)")
+        body = np.frombuffer(data, np.uint8)[14:]
+        rows = np.ascontiguousarray(rows, np.uint64).reshape(nframes, self.h // 16)
+        full, tail = divmod(nframes, ip)
+        so, sb = np.zeros(1, np.uint64), np.array([body.size], np.uint64)
+        outs = []
+        if full:
+            outs.append(self.decode_streams(body, so, sb, rows[: full * ip], 1, full, ip, qdc, qac))
+        if tail:
+            outs.append(self.decode_streams(body, so, sb, rows[full * ip:], 1, 1, tail, qdc, qac))
+        return np.concatenate(outs)
 
     # ---- decoder -----------------------------------------------------------------------------------
     def decode_gops(self, levels, mpm, ipm, mvd, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int,
@@ -236,6 +265,33 @@ class IcspCuda:
         if out is None:
             out = np.zeros((n, self.fb), np.uint8)
         self._chk(self.lib.icsp_decode_gops(self.h_ctx, C.byref(din), n_gops, gop_len, qp_dc, qp_ac, _ptr(out)), "icsp_decode_gops")
+        return out
+
+    # ---- decoder with the bit reader on the GPU (SURVEY §8 f3) ---------------------------------------
+    def bits_row_index(self, n_frames: int) -> np.ndarray:
+        """[n_frames][mbh] uint64 bit offset of every macroblock row inside its stream's body, for what
+        encode_streams / entropy_run just coded."""
+        rows = np.zeros((n_frames, self.h // 16), np.uint64)
+        self._chk(self.lib.icsp_bits_row_index(self.h_ctx, n_frames, _ptr(rows)), "icsp_bits_row_index")
+        return rows
+
+    def decode_streams(self, bits: np.ndarray, stream_offset, stream_bytes, row_bit_offset, n_streams: int, gops_per_stream: int,
+                       gop_len: int, qp_dc: int, qp_ac: int, out: np.ndarray | None = None) -> np.ndarray:
+        """bodies (file bytes after the 14-byte header) + macroblock-row index in, decoded I420 frames out."""
+        n = n_streams * gops_per_stream * gop_len
+        bits = np.ascontiguousarray(bits, np.uint8)
+        so = np.ascontiguousarray(stream_offset, np.uint64)
+        sb = np.ascontiguousarray(stream_bytes, np.uint64)
+        ro = np.ascontiguousarray(row_bit_offset, np.uint64)
+        if so.size != n_streams or sb.size != n_streams or ro.size != n * (self.h // 16):
+            raise IcspError("decode_streams: table sizes do not match the stream geometry")
+        if int(so[-1] + sb[-1]) > bits.size:
+            raise IcspError("decode_streams: stream table points past the bits buffer")
+        if out is None:
+            out = np.zeros((n, self.fb), np.uint8)
+        din = _lib.DecBitsIn(_ptr(bits), _ptr(so), _ptr(sb), _ptr(ro))
+        self._chk(self.lib.icsp_decode_streams(self.h_ctx, C.byref(din), n_streams, gops_per_stream, gop_len, qp_dc, qp_ac, _ptr(out)),
+                  "icsp_decode_streams")
         return out
 
     def decode_sequence(self, levels, mpm, ipm, mvd, qp_dc: int, qp_ac: int, intra_period: int) -> np.ndarray:

@@ -235,4 +235,114 @@ __global__ void __launch_bounds__(EN_THREADS) entropy_pack_kernel(Geom g, FrameP
     sink.flush();
 }
 
+// =====================================================================================================
+// f3 of SURVEY.md §8: the decoder's bit reader (readBlockData + DC/AC/MVientropy, DEC:38-2025) on the GPU.
+// The format has no resynchronisation points (nothing is byte aligned, no start codes), so a bare stream is one serial
+// VLC chain.  The encoder, however, knows where everything starts: (2a)/(2b) above are exactly the bit offsets of every
+// block.  row_index_kernel exports the offset of every MACROBLOCK ROW (8 bytes per row: 0.4 % of the stream, the
+// "<bin>.idx" side-car of icspenc --index); with it parse_rows_kernel runs one independent chain per (frame, MB row):
+// 19 200 CIF frames = 345 600 threads instead of 64.  Without an index the C++ parser (host/bitstream.cpp) is used.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) row_index_kernel(Geom g, EntropyPtrs e, unsigned long long* __restrict__ rows, int n_frames)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_frames * g.mbh) return;
+    const int f = i / g.mbh, y = i - f * g.mbh;
+    rows[i] = e.framebits[f] + e.blkbits[(size_t)f * g.nmb * 6 + (size_t)y * g.mbw * 6];
+}
+
+// MSB-first bit source over a stream body in global memory.  `buf` holds `nb` (> 32 between calls) valid bits, left
+// aligned.  Bits at or after 8*nbytes read as 0, like the host reader.
+struct BitSource {
+    const uint32_t* w;
+    unsigned long long nbytes, widx, buf;
+    int nb;
+    __device__ __forceinline__ uint32_t fetch()
+    {
+        uint32_t v = 0;
+        if (widx * 4 < nbytes) {
+            v = __byte_perm(__ldg(w + widx), 0, 0x0123);
+            const unsigned long long rem = nbytes - widx * 4;           // valid bytes in this word
+            if (rem < 4) v &= 0xffffffffu << (8 * (4 - (int)rem));
+        }
+        widx++;
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t* body, unsigned long long nbytes_, unsigned long long pos)
+    {
+        w = (const uint32_t*)body; nbytes = nbytes_; widx = pos >> 5;
+        const int sh = (int)(pos & 31);
+        const uint32_t a = fetch(), b = fetch();
+        buf = (((unsigned long long)a << 32) | b) << sh;
+        nb = 64 - sh;
+        if (nb <= 32) { buf |= (unsigned long long)fetch() << (32 - nb); nb += 32; }
+    }
+    __device__ __forceinline__ uint32_t top() const { return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ void skip(int k)                          // k <= 32
+    {
+        buf <<= k; nb -= k;
+        if (nb <= 32) { buf |= (unsigned long long)fetch() << (32 - nb); nb += 32; }
+    }
+    __device__ __forceinline__ int bit() { const int v = (int)(buf >> 63); skip(1); return v; }
+    // DCientropy (DEC:407-608) and its AC / MV twins: 3-bit category prefix, unary extension from category 6 up
+    __device__ __forceinline__ int vlc()
+    {
+        const uint32_t t = top();
+        const uint32_t top3 = t >> 29;
+        if (top3 < 2) { skip(2); return 0; }
+        if (top3 == 2) { skip(4); return (t >> 28) & 1 ? 1 : -1; }
+        int e, prefix;
+        if (top3 != 7) { e = (int)top3 - 2; prefix = 3; }
+        else {
+            const int ones = __clz((int)~t);
+            if (ones >= 10) return 0;              // no category matches: the reference leaves len = 0, val = 0
+            e = ones + 2; prefix = ones + 1;
+        }
+        const int sgn = (int)((t >> (31 - prefix)) & 1u);
+        const int rem = (int)((t << (prefix + 1)) >> (32 - e));          // prefix + 1 + e <= 22 bits
+        skip(prefix + 1 + e);
+        const int v = (1 << e) + rem;
+        return sgn ? v : -v;
+    }
+};
+
+struct ParsePtrs {
+    const uint8_t* bits;                    // bodies (file bytes after the 14-byte header)
+    const unsigned long long* streamoff;    // [S] byte offset of each body inside bits (multiple of 4)
+    const unsigned long long* streambytes;  // [S] body length in bytes
+    const unsigned long long* rows;         // [F][mbh] bit offset of every MB row from its body start
+};
+// one thread per (frame, macroblock row); levels must be pre-zeroed (only non-zero levels are stored)
+__global__ void __launch_bounds__(64) parse_rows_kernel(Geom g, FramePtrs p, ParsePtrs q, int gop_len, int frames_per_stream,
+                                                        int s_first, int n_frames)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x;
+    if (i >= n_frames * g.mbh) return;
+    const int f = i / g.mbh, y = i - f * g.mbh;       // f: frame inside the chunk (p.* are chunk-relative)
+    const int s = s_first + f / frames_per_stream;
+    const bool intra = (f % gop_len) == 0;
+    BitSource b;
+    b.init(q.bits + q.streamoff[s], q.streambytes[s], q.rows[i]);
+    for (int mbx = 0; mbx < g.mbw; mbx++) {
+        const size_t m = (size_t)f * g.nmb + (size_t)y * g.mbw + mbx;
+        if (!intra) {
+            b.skip(1);                                                  // MVmodeflag (DEC:301)
+            const int mx = b.vlc(), my = b.vlc();
+            *(uint32_t*)(p.mvd + m * 2) = ((uint32_t)mx & 0xffffu) | ((uint32_t)my << 16);
+        }
+        for (int k = 0; k < 6; k++) {
+            if (intra && k < 4) { p.mpm[m * 4 + k] = (uint8_t)b.bit(); p.ipm[m * 4 + k] = (uint8_t)b.bit(); }
+            int16_t* zz = p.levels + (m * 6 + k) * 64;
+            const int dc = b.vlc();
+            if (dc) zz[0] = (int16_t)dc;
+            if (b.bit()) { b.skip(31); b.skip(32); continue; }          // ACflag: 63 zero bits follow
+            for (int c = 1; c < 64;) {
+                const int z = min(__clz((int)b.top()) >> 1, min(16, 64 - c));   // run of "00" symbols
+                if (z) { b.skip(2 * z); c += z; }
+                if (c < 64) { const int v = b.vlc(); if (v) zz[c] = (int16_t)v; c++; }
+            }
+        }
+    }
+}
+
 }  // namespace icsp

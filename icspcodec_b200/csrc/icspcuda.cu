@@ -23,14 +23,14 @@ thread_local char g_create_error[256] = "";
 enum KernelId {
     K_INTRA_ENC = 0, K_INTRA_DEC, K_FDCT, K_DCCHAIN, K_IDCT_ENC, K_IDCT_DEC, K_ME_SAD, K_ME_ZERO, K_ME_CHAIN, K_ME_FIXUP,
     K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_EN_SIZE, K_EN_FSCAN, K_EN_SSCAN, K_EN_ZERO, K_EN_PACK, K_FDCT_C, K_IDCT_ENC_C,
-    K_IDCT_DEC_C, K_SSE, K_COUNT
+    K_IDCT_DEC_C, K_SSE, K_ROWIDX, K_PARSE, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "intra_luma_kernel<enc>", "intra_luma_kernel<dec>", "fdct_quant_kernel", "dc_chain_kernel", "idct_recon_kernel<enc>",
     "idct_recon_kernel<dec>", "me_sad_kernel", "me_zero_kernel", "me_chain_kernel", "me_sad_kernel(fixup)",
     "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel", "entropy_size_kernel", "entropy_frame_scan_kernel",
     "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel", "fdct_quant_kernel(intra: chroma only)",
-    "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)", "plane_sse_kernel"};
+    "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)", "plane_sse_kernel", "row_index_kernel", "parse_rows_kernel"};
 
 struct Pending { int k; cudaEvent_t a, b; };
 
@@ -67,6 +67,7 @@ struct icsp_ctx {
     unsigned long long *d_framebits = nullptr, *d_streambits = nullptr, *d_streamoff = nullptr, *d_chunktotal = nullptr;
     uint32_t* d_overflow = nullptr;
     uint8_t* d_bits = nullptr;
+    unsigned long long* d_rows = nullptr;     // [cap][mbh] macroblock-row bit offsets (row index / GPU bit reader)
     unsigned long long* d_sse = nullptr;      // [cap][3] plane SSE (allocated on first use)
     unsigned long long* h_tables = nullptr;   // pinned: [cap] stream bits, [cap] stream offsets, [64] chunk totals, [64] overflow
     struct EnChunk { int s0, ns; size_t f0, nf; unsigned long long region_off, region_cap; };
@@ -348,13 +349,21 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
         const int per = TR_THREADS / 8;
         dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
         if (st.intra) {
-            LaunchScope ls(c, K_INTRA_DEC, s);
-            intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, s>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr);
+            int hi;
+            cudaStream_t h = hi_begin(c, s, hi);
+            { LaunchScope ls(c, K_INTRA_DEC, h);
+              intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr); }
+            hi_end(c, s, hi);
         } else {
             LaunchScope ls(c, K_MV_RECON, s);
             mv_recon_kernel<<<G, 32, 0, s>>>(g, p, st);
         }
-        { LaunchScope ls(c, K_DCCHAIN, s); dc_chain_kernel<<<G, 128, c->chain_smem, s>>>(g, p, st, 1, c->chain_staged); }
+        {
+            int hi;
+            cudaStream_t h = hi_begin(c, s, hi);
+            { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 1, c->chain_staged); }
+            hi_end(c, s, hi);
+        }
         { LaunchScope ls(c, st.intra ? K_IDCT_DEC_C : K_IDCT_DEC, s); idct_recon_kernel<1><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
     }
     return ICSP_OK;
@@ -572,7 +581,7 @@ void icsp_destroy(icsp_ctx* c)
     for (auto& s : c->slots) if (s) cudaEventDestroy(s);
     void* bufs[] = {c->d_cur, c->d_rec, c->d_levels, c->d_acflag, c->d_mpm, c->d_ipm, c->d_mvd, c->d_mv, c->d_minsad, c->d_dcraw,
                     c->d_dcrec, c->d_mestate, c->d_memoves, c->d_meflag, c->d_mezero, c->d_shim, c->d_blkbits, c->d_framebits,
-                    c->d_streambits, c->d_streamoff, c->d_chunktotal, c->d_overflow, c->d_bits, c->d_intra_edges, c->d_sse};
+                    c->d_streambits, c->d_streamoff, c->d_chunktotal, c->d_overflow, c->d_bits, c->d_intra_edges, c->d_sse, c->d_rows};
     if (c->h_tables) cudaFreeHost(c->h_tables);
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -834,6 +843,25 @@ int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int g
     return icsp_sync(c);
 }
 
+// macroblock-row index of what icsp_encode_streams / icsp_entropy_run just coded (SURVEY.md §8 f3 side-car)
+int icsp_bits_row_index(icsp_ctx* c, int n_frames, uint64_t* rows)
+{
+    if (!c || !rows || n_frames <= 0) return fail(c, ICSP_ERR_PARAM, "icsp_bits_row_index: bad arguments");
+    if (c->en_chunks.empty()) return fail(c, ICSP_ERR_PARAM, "icsp_bits_row_index: nothing was entropy coded");
+    const auto& last = c->en_chunks.back();
+    if ((size_t)n_frames > last.f0 + last.nf) return fail(c, ICSP_ERR_PARAM, "icsp_bits_row_index: only %zu frames were entropy coded", last.f0 + last.nf);
+    CU(cudaSetDevice(c->device));
+    const Geom& g = c->g;
+    if (!c->d_rows) CU(cudaMalloc(&c->d_rows, (size_t)c->cap * g.mbh * sizeof(unsigned long long)));
+    EntropyPtrs e{};
+    e.blkbits = c->d_blkbits; e.framebits = c->d_framebits;
+    const int n = n_frames * g.mbh;
+    { LaunchScope ls(c, K_ROWIDX, c->stream); row_index_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(g, e, c->d_rows, n_frames); }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rows, c->d_rows, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    return icsp_sync(c);
+}
+
 // ---- decoder -------------------------------------------------------------------------------------------
 int icsp_dec_upload(icsp_ctx* c, const icsp_dec_in* in, int n)
 {
@@ -1021,6 +1049,73 @@ int icsp_configure(icsp_ctx* c, int n_compute_streams, int chunk_gops_)
     c->n_cstreams = n_compute_streams;
     c->chunk_gops_target = chunk_gops_;
     return ICSP_OK;
+}
+
+// ---- decoder with the bit reader on the GPU ------------------------------------------------
+int icsp_decode_streams(icsp_ctx* c, const icsp_dec_bits_in* in, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
+                        uint8_t* out)
+{
+    int rc = check_streams(c, n_streams, gops_per_stream, gop_len);
+    if (rc) return rc;
+    if ((rc = check_run(c, n_streams * gops_per_stream, gop_len, qdc, qac))) return rc;
+    if (!in || !in->bits || !in->stream_offset || !in->stream_bytes || !in->row_bit_offset || !out)
+        return fail(c, ICSP_ERR_PARAM, "icsp_decode_streams: bad arguments");
+    CU(cudaSetDevice(c->device));
+    if ((rc = entropy_alloc(c))) return rc;
+    const Geom& g = c->g;
+    const size_t nmb = (size_t)g.nmb;
+    if (!c->d_rows) CU(cudaMalloc(&c->d_rows, (size_t)c->cap * g.mbh * sizeof(unsigned long long)));
+    const int fps = gops_per_stream * gop_len;
+    const size_t cap_bytes = (size_t)c->cap * en_frame_cap(g);
+    for (int s = 0; s < n_streams; s++) {      // bodies in stream order, 4-byte aligned starts, inside the device region
+        const uint64_t o = in->stream_offset[s], b = in->stream_bytes[s];
+        if ((o & 3) || o + b > cap_bytes || (s && o < in->stream_offset[s - 1] + in->stream_bytes[s - 1]))
+            return fail(c, ICSP_ERR_PARAM, "icsp_decode_streams: stream %d: offsets must ascend, be multiples of 4 and fit the context", s);
+        for (int r = 0; r < fps * g.mbh; r++)
+            if (in->row_bit_offset[(size_t)s * fps * g.mbh + r] > b * 8) return fail(c, ICSP_ERR_PARAM, "icsp_decode_streams: stream %d: row index beyond the body", s);
+    }
+    // the (validated) tables go up first, on the main stream
+    unsigned long long* h_off = c->h_tables;                       // pinned staging: [cap] offsets, [cap] lengths
+    unsigned long long* h_len = c->h_tables + c->cap;
+    for (int s = 0; s < n_streams; s++) { h_off[s] = in->stream_offset[s]; h_len[s] = in->stream_bytes[s]; }
+    CU(cudaMemcpyAsync(c->d_streamoff, h_off, n_streams * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_streambits, h_len, n_streams * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->s_up, c->ev_fork, 0));
+    for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
+    CU(cudaStreamWaitEvent(c->s_down, c->ev_fork, 0));
+    // software pipeline over chunks of whole streams: H2D of bodies + row index | parse + reconstruction | D2H of the frames
+    const int cs = chunk_streams(c, n_streams, gops_per_stream, true);
+    for (int s0 = 0, i = 0; s0 < n_streams; s0 += cs, i++) {
+        const int ns = std::min(cs, n_streams - s0);
+        const size_t f0 = (size_t)s0 * fps, cnt = (size_t)ns * fps;
+        cudaStream_t st = c->cstream[i % c->n_cstreams];
+        const uint64_t b0 = in->stream_offset[s0], b1 = in->stream_offset[s0 + ns - 1] + in->stream_bytes[s0 + ns - 1];
+        CU(cudaMemcpyAsync(c->d_bits + b0, in->bits + b0, b1 - b0, cudaMemcpyHostToDevice, c->s_up));
+        CU(cudaMemcpyAsync(c->d_rows + f0 * g.mbh, in->row_bit_offset + f0 * g.mbh, cnt * g.mbh * sizeof(uint64_t), cudaMemcpyHostToDevice, c->s_up));
+        cudaEvent_t up = chunk_event(c, 2 * i), done = chunk_event(c, 2 * i + 1);
+        CU(cudaEventRecord(up, c->s_up));
+        CU(cudaMemsetAsync(c->d_levels + f0 * nmb * 384, 0, cnt * nmb * 384 * sizeof(int16_t), st));   // the parser stores non-zero levels only
+        CU(cudaStreamWaitEvent(st, up, 0));
+        {
+            FramePtrs p = frame_ptrs(c, (int)(f0 / gop_len), gop_len);
+            ParsePtrs q{c->d_bits, c->d_streamoff, c->d_streambits, c->d_rows + f0 * g.mbh};
+            const int n = (int)cnt * g.mbh;
+            LaunchScope ls(c, K_PARSE, st);
+            parse_rows_kernel<<<(n + 63) / 64, 64, 0, st>>>(g, p, q, gop_len, fps, s0, (int)cnt);
+        }
+        if ((rc = decode_chunk(c, s0 * gops_per_stream, ns * gops_per_stream, gop_len, qdc, qac, st))) return rc;
+        CU(cudaEventRecord(done, st));
+        CU(cudaStreamWaitEvent(c->s_down, done, 0));
+        CU(cudaMemcpyAsync(out + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, c->s_down));
+    }
+    if ((rc = join_streams(c))) return rc;
+    CU(cudaEventRecord(c->ev_join[0], c->s_down));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
+    CU(cudaEventRecord(c->ev_join[1], c->s_up));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+    CU(cudaGetLastError());
+    return icsp_sync(c);
 }
 
 // ---- quality numbers without the reconstruction read-back ----------------------------------

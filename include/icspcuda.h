@@ -124,6 +124,12 @@ int icsp_entropy_run(icsp_ctx* ctx, int n_streams, int gops_per_stream, int gop_
 int icsp_bits_download(icsp_ctx* ctx, int n_streams, const icsp_bits_out* out);   /* synchronous */
 /* In place: turns an MSB-first body of nbits bits (buffer must hold nbits/8+1 bytes) into the reference's file body;
  * returns its length nbits/8+1. */
+/* Macroblock-row index of what icsp_encode_streams / icsp_entropy_run just coded: rows[f*(height/16) + y]
+ * = bit offset, from the start of its stream's body, of the first macroblock of row y of frame f (f < n_frames, frames in
+ * the order of the call).  8 bytes per row (0.4 % of a CIF stream); icspenc --index stores it as "<bin>.idx".  The stream
+ * format has no resynchronisation points (DEC:38-404 is one serial VLC chain); with this index every macroblock row is an
+ * independent chain and icsp_decode_streams parses on the GPU.  Synchronous. */
+int icsp_bits_row_index(icsp_ctx* ctx, int n_frames, uint64_t* rows);
 size_t icsp_finish_body(uint8_t* body, uint64_t nbits);
 /* worst-case size in bytes of the packed bodies of n_frames frames (any content, any QP), incl. alignment slack */
 size_t icsp_bits_bound(int width, int height, int n_frames);
@@ -134,6 +140,24 @@ int icsp_decode_gops(icsp_ctx* ctx, const icsp_dec_in* in, int n_gops, int gop_l
 int icsp_dec_upload(icsp_ctx* ctx, const icsp_dec_in* in, int n_frames);
 int icsp_dec_run(icsp_ctx* ctx, int n_gops, int gop_len, int qp_dc, int qp_ac);
 int icsp_dec_download(icsp_ctx* ctx, int n_frames, uint8_t* i420_out);
+
+/* ---- decoder with the bit reader on the GPU ------------------------------------------ */
+/* Replaces readBlockData + DC/AC/MVientropy (DEC:38-2025) AND intraPredictionDecode / interPredictionDecode for a batch of
+ * independent streams whose macroblock-row index is known: bodies in (file bytes after the 14-byte header, including the
+ * reference's right-aligned last byte, ENC:4895), decoded I420 out.  One GPU thread parses one macroblock row.
+ *   bits            bodies, stream s at bits + stream_offset[s] (offsets ascending, multiples of 4), stream_bytes[s] long
+ *   row_bit_offset  [n_frames][height/16], see icsp_bits_row_index (offsets of a tail GOP decoded by a second call must be
+ *                   passed relative to the same body start)
+ *   out             [n_frames][fb]
+ * A wrong index yields wrong pictures, never out-of-bounds accesses (offsets are validated, reads past a body return 0). */
+typedef struct icsp_dec_bits_in {
+    const uint8_t* bits;
+    const uint64_t* stream_offset;   /* [n_streams] */
+    const uint64_t* stream_bytes;    /* [n_streams] */
+    const uint64_t* row_bit_offset;  /* [n_streams*gops_per_stream*gop_len][height/16] */
+} icsp_dec_bits_in;
+int icsp_decode_streams(icsp_ctx* ctx, const icsp_dec_bits_in* in, int n_streams, int gops_per_stream, int gop_len, int qp_dc,
+                        int qp_ac, uint8_t* out);
 
 /* ---- kernel-level shims (unit parity + micro-benchmarks); host pointers, synchronous ---------------- */
 /* motionEstimation (ENC:2073-2155): n frame pairs, luma planes only [n][w*h]; carried spiral state per frame */
