@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libicspcuda.so")
 
 ICSP_OK = 0
-MAX_KERNELS = 24
+MAX_KERNELS = 32
 
 
 class EncOut(C.Structure):

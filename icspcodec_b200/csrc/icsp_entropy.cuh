@@ -256,26 +256,34 @@ __global__ void __launch_bounds__(128) row_index_kernel(Geom g, EntropyPtrs e, u
 struct BitSource {
     const uint32_t* w;
     unsigned long long nbytes, widx, buf;
+    uint32_t nx0, nx1;      // the next two words, already loaded: the global-memory latency of a refill overlaps ~64 bits of parsing
     int nb;
-    __device__ __forceinline__ uint32_t fetch()
+    __device__ __forceinline__ uint32_t load(unsigned long long i) const
     {
         uint32_t v = 0;
-        if (widx * 4 < nbytes) {
-            v = __byte_perm(__ldg(w + widx), 0, 0x0123);
-            const unsigned long long rem = nbytes - widx * 4;           // valid bytes in this word
+        if (i * 4 < nbytes) {
+            v = __byte_perm(__ldg(w + i), 0, 0x0123);
+            const unsigned long long rem = nbytes - i * 4;              // valid bytes in this word
             if (rem < 4) v &= 0xffffffffu << (8 * (4 - (int)rem));
         }
-        widx++;
+        return v;
+    }
+    __device__ __forceinline__ uint32_t fetch()
+    {
+        const uint32_t v = nx0;
+        nx0 = nx1;
+        nx1 = load(widx++);
         return v;
     }
     __device__ __forceinline__ void init(const uint8_t* body, unsigned long long nbytes_, unsigned long long pos)
     {
         w = (const uint32_t*)body; nbytes = nbytes_; widx = pos >> 5;
         const int sh = (int)(pos & 31);
-        const uint32_t a = fetch(), b = fetch();
+        const uint32_t a = load(widx), b = load(widx + 1);
+        nx0 = load(widx + 2); nx1 = load(widx + 3);
+        widx += 4;
         buf = (((unsigned long long)a << 32) | b) << sh;
         nb = 64 - sh;
-        if (nb <= 32) { buf |= (unsigned long long)fetch() << (32 - nb); nb += 32; }
     }
     __device__ __forceinline__ uint32_t top() const { return (uint32_t)(buf >> 32); }
     __device__ __forceinline__ void skip(int k)                          // k <= 32

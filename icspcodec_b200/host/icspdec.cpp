@@ -2,13 +2,17 @@
 // (IcspCodec::decoding, DEC.h:290-313) on the host, the reconstruction core (intraPredictionDecode /
 // interPredictionDecode, DEC:2083-2272) on the GPU through libicspcuda (binary64 cosine table, DEC.h:19).
 //
-//   icspdec <nframes> <stream.bin> <QPDC> <QPAC> <intraPeriod> [<original.yuv>] [--gpus G] [--out file]
+//   icspdec <nframes> <stream.bin> <QPDC> <QPAC> <intraPeriod> [<original.yuv>] [--gpus G] [--out file] [--index file | --no-index]
+//
+// When <stream.bin>.idx exists (icspenc --index: the bit offset of every macroblock row) the bit reader runs on the GPU too
+// (icsp_decode_streams); otherwise the stream is parsed serially on the host (bitstream.cpp) as the reference does.
 //
 // QP / intraPeriod / size are taken from the stream header like the reference does (the positional values are
 // accepted for CLI compatibility).  Output: check_test_intra_yuv.yuv when intraPeriod == 1, otherwise
 // check_test_inter_yuv.yuv (DEC:4476-4527); with an original YUV the average luma PSNR and the decode time are
 // appended to experimental_Result_Decoding.txt (DEC.h:315-355).  The reference opens "output\\<bin>" and
 // "data\\<yuv>" with literal backslashes (DEC.h:241,323); both spellings are tried.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -32,10 +36,13 @@ int main(int argc, char** argv)
 {
     std::vector<std::string> pos;
     int gpus = 1;
-    std::string outname;
+    std::string outname, idxname;
+    bool use_index = true;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
+        else if (a == "--index" && i + 1 < argc) idxname = argv[++i];
+        else if (a == "--no-index") use_index = false;
         else if (a == "--out" && i + 1 < argc) outname = argv[++i];
         else pos.push_back(a);
     }
@@ -48,8 +55,26 @@ int main(int argc, char** argv)
     { uint8_t buf[1 << 16]; size_t r; while ((r = fread(buf, 1, sizeof(buf), fb_)) > 0) file.insert(file.end(), buf, buf + r); }
     fclose(fb_);
 
+    // macroblock-row index side-car: "ICSPIDX1", width, height, frames, macroblock rows (u32 LE), u64 LE bit offsets
+    std::vector<uint64_t> index;
+    if (use_index) {
+        FILE* fx = idxname.empty() ? open_either(pos[1] + ".idx", "output\\" + pos[1] + ".idx") : fopen(idxname.c_str(), "rb");
+        if (fx) {
+            char magic[8]; uint32_t hdr[4];
+            if (fread(magic, 1, 8, fx) == 8 && !memcmp(magic, "ICSPIDX1", 8) && fread(hdr, 4, 4, fx) == 4 && hdr[2] >= (uint32_t)nframes &&
+                hdr[3] == hdr[1] / 16) {
+                index.resize((size_t)nframes * hdr[3]);
+                if (fread(index.data(), 8, index.size(), fx) != index.size()) index.clear();
+                if (!index.empty() && file.size() >= 14 &&
+                    (hdr[0] != (uint32_t)(file[7] | (file[8] << 8)) || hdr[1] != (uint32_t)(file[5] | (file[6] << 8)))) index.clear();
+            }
+            fclose(fx);
+            if (index.empty()) fprintf(stderr, "icspdec: index does not match the stream, parsing on the host\n");
+        } else if (!idxname.empty()) { fprintf(stderr, "[ERROR] cannot open %s\n", idxname.c_str()); return 1; }
+    }
+    const bool gpu_parse = !index.empty();
     icsp_host::ParsedStream ps;
-    try { ps = icsp_host::parse_stream(file, nframes); }
+    try { ps = icsp_host::parse_stream(file, gpu_parse ? 0 : nframes); }     // 0 frames: header only
     catch (const std::exception& e) { fprintf(stderr, "[ERROR] %s\n", e.what()); return 1; }
     const int w = ps.p.width, h = ps.p.height, ip = ps.p.intra_period, nmb = (w / 16) * (h / 16);
     const size_t fbytes = (size_t)w * h * 3 / 2;
@@ -74,8 +99,20 @@ int main(int argc, char** argv)
         for (int g = 0; g < s.n_gops && !s.rc; g += per_call) {
             const int ng = std::min(per_call, s.n_gops - g);
             const size_t f0 = (size_t)s.first + (size_t)g * s.gop_len;
-            icsp_dec_in in{ps.levels.data() + f0 * nmb * 384, ps.mpm.data() + f0 * nmb * 4, ps.ipm.data() + f0 * nmb * 4, ps.mvd.data() + f0 * nmb * 2};
-            s.rc = icsp_decode_gops(ctx, &in, ng, s.gop_len, ps.p.qp_dc, ps.p.qp_ac, yuv.data() + f0 * fbytes);
+            if (gpu_parse) {   // only the bytes of these frames travel: [first row of f0, first row of the frame after the call)
+                const size_t mbh = (size_t)h / 16, f1 = f0 + (size_t)ng * s.gop_len, body = file.size() - 14;
+                const uint64_t start = (index[f0 * mbh] / 8) & ~(uint64_t)3;
+                const uint64_t end = f1 < (size_t)nframes ? std::min<uint64_t>(body, index[f1 * mbh] / 8 + 1) : body;
+                if (start > end) { s.rc = ICSP_ERR_PARAM; s.err = "row index is not ascending"; break; }
+                std::vector<uint64_t> rows(index.begin() + (long)(f0 * mbh), index.begin() + (long)(f1 * mbh));
+                for (auto& r : rows) r -= start * 8;
+                const uint64_t off = 0, len = end - start;
+                icsp_dec_bits_in in{file.data() + 14 + start, &off, &len, rows.data()};
+                s.rc = icsp_decode_streams(ctx, &in, 1, ng, s.gop_len, ps.p.qp_dc, ps.p.qp_ac, yuv.data() + f0 * fbytes);
+            } else {
+                icsp_dec_in in{ps.levels.data() + f0 * nmb * 384, ps.mpm.data() + f0 * nmb * 4, ps.ipm.data() + f0 * nmb * 4, ps.mvd.data() + f0 * nmb * 2};
+                s.rc = icsp_decode_gops(ctx, &in, ng, s.gop_len, ps.p.qp_dc, ps.p.qp_ac, yuv.data() + f0 * fbytes);
+            }
             if (s.rc) s.err = icsp_last_error(ctx);
         }
         icsp_destroy(ctx);
@@ -116,6 +153,7 @@ int main(int argc, char** argv)
             }
         }
     }
-    fprintf(stderr, "icspdec: %d frames %dx%d decoded in %.3f s (%.0f fps) -> %s\n", nframes, w, h, secs, nframes / secs, outname.c_str());
+    fprintf(stderr, "icspdec: %d frames %dx%d decoded in %.3f s (%.0f fps, bit reader on the %s) -> %s\n", nframes, w, h, secs, nframes / secs,
+            gpu_parse ? "GPU" : "host", outname.c_str());
     return 0;
 }

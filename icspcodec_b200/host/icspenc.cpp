@@ -3,7 +3,7 @@
 // core (intraPrediction / interPrediction) on the GPU through libicspcuda, then the host bitstream writer.
 //
 //   icspenc -i <name_cif.yuv> -n <frames> [-q Q | --qpdc D --qpac A] [--intraPeriod P] [-w W -h H]
-//           [--EnMultiThread T] [--gpus G] [--no-recon] [--psnr] [--quiet]
+//           [--EnMultiThread T] [--gpus G] [--no-recon] [--psnr] [--index] [--quiet]
 //
 // Outputs, like the reference: <prefix>_compCIF_<QDC>_<QAC>_<IP>.bin (prefix = input name up to the first '_',
 // encoder_main.cpp:10-17) and test_yuv.yuv (reconstruction, ENC:6376-6421).  Unlike the reference's
@@ -28,6 +28,7 @@ struct Options {
     int qdc = 0, qac = 0, ip = 0, threads = 0, gpus = 1;
     int width = 352, height = 288;  // encoder_main.cpp:20 hard-wires CIF; -w/-h are accepted here
     bool recon = true, quiet = false;
+    bool index = false;         // --index: write <bin>.idx, the macroblock-row index icspdec uses to parse on the GPU
     bool psnr = false;          // --psnr: luma PSNR of the reconstruction, reduced on the GPU (what the reference's decoder logs, DEC.h:332-350)
     bool host_entropy = false;  // --host-entropy: download the syntax arrays and entropy-code on the CPU (round-1 path)
 };
@@ -66,6 +67,7 @@ int parse(int argc, char** argv, Options& o)
         else if (a == "--no-recon") o.recon = false;
         else if (a == "--host-entropy") o.host_entropy = true;
         else if (a == "--psnr") o.psnr = true;
+        else if (a == "--index") o.index = true;
         else if (a == "--quiet") o.quiet = true;
         else if (a[0] == '-') { fprintf(stderr, "[ERROR] uncorrect parameters in parsing_command\n"); return -1; }
     }
@@ -79,6 +81,7 @@ struct Shard {          // one GPU's contiguous range of GOPs
     std::string err;
     std::vector<std::pair<std::vector<uint8_t>, uint64_t>> bits;   // GPU entropy path: MSB-first bit strings, in order
     std::vector<uint64_t> sse;  // --psnr: [frames][3]
+    std::vector<std::vector<uint64_t>> rows;   // --index: per segment, [frames][mbh] bit offsets inside the segment
 };
 }  // namespace
 
@@ -91,6 +94,7 @@ int main(int argc, char** argv)
         fprintf(stderr, "[ERROR] uncorrect parameters (need -i, -n > 0, QP in 1..255, intraPeriod in 0..63, width/height multiples of 16)\n");
         return 1;
     }
+    if (o.index && o.host_entropy) { fprintf(stderr, "[ERROR] --index needs the GPU entropy coder (drop --host-entropy)\n"); return 1; }
     const size_t us = o.input.find('_');
     if (us == std::string::npos) { fprintf(stderr, "[ERROR] input file name must contain '_' (encoder_main.cpp:13)\n"); return 1; }
     const std::string slash_stripped = o.input.substr(0, us);
@@ -129,9 +133,9 @@ int main(int argc, char** argv)
     std::vector<Shard> shards;
     for (int d = 0; d < G; d++) {
         const int g0 = (int)((long long)full * d / G), g1 = (int)((long long)full * (d + 1) / G);
-        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, "", {}, {}});
+        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, "", {}, {}, {}});
     }
-    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}, {}});
+    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}, {}, {}});
     auto run_shard = [&](Shard& s) {
         const int cnt = s.n_gops * s.gop_len;
         int call_frames = 4096;                                    // bound device memory per call
@@ -153,6 +157,11 @@ int main(int argc, char** argv)
                 uint64_t nbits = 0, off = 0;
                 icsp_bits_out bo{buf.data(), cap, &nbits, &off, recon ? recon + f0 * fb : nullptr};
                 s.rc = icsp_encode_streams(ctx, frames + f0 * fb, 1, ng, s.gop_len, o.qdc, o.qac, &bo);
+                if (!s.rc && o.index) {
+                    std::vector<uint64_t> r((size_t)ng * s.gop_len * (o.height / 16));
+                    s.rc = icsp_bits_row_index(ctx, ng * s.gop_len, r.data());
+                    s.rows.push_back(std::move(r));
+                }
                 if (!s.rc) {
                     buf.erase(buf.begin(), buf.begin() + (long)off);
                     buf.resize((size_t)((nbits + 7) / 8));
@@ -192,8 +201,23 @@ int main(int argc, char** argv)
     } else {   // concatenate the per-shard bit strings in frame order (frames are not byte aligned in the stream, H7)
         std::sort(shards.begin(), shards.end(), [](const Shard& a, const Shard& b) { return a.first_frame < b.first_frame; });
         icsp_host::BitString all;
+        std::vector<uint64_t> index;
+        uint64_t base = 0;
         for (auto& s : shards)
-            for (auto& seg : s.bits) all.append_msb_bytes(seg.first.data(), seg.second);
+            for (size_t i = 0; i < s.bits.size(); i++) {
+                all.append_msb_bytes(s.bits[i].first.data(), s.bits[i].second);
+                if (o.index) for (uint64_t r : s.rows[i]) index.push_back(base + r);
+                base += s.bits[i].second;
+            }
+        if (o.index) {   // side-car: "ICSPIDX1", width, height, frames, macroblock rows (u32 LE), then u64 LE bit offsets from the body start
+            char iname[520];
+            snprintf(iname, sizeof(iname), "%s_compCIF_%d_%d_%d.bin.idx", slash_stripped.c_str(), o.qdc, o.qac, o.ip);
+            FILE* fx = fopen(iname, "wb");
+            if (!fx) { fprintf(stderr, "fail to open %s\n", iname); return 1; }
+            const uint32_t hdr[4] = {(uint32_t)o.width, (uint32_t)o.height, (uint32_t)n, (uint32_t)(o.height / 16)};
+            fwrite("ICSPIDX1", 1, 8, fx); fwrite(hdr, 4, 4, fx); fwrite(index.data(), 8, index.size(), fx);
+            fclose(fx);
+        }
         bin = icsp_host::stream_header(sp);
         const std::vector<uint8_t> body = all.reference_body();
         bin.insert(bin.end(), body.begin(), body.end());

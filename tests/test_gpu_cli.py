@@ -124,3 +124,26 @@ def test_icspenc_psnr_on_gpu(tmp_path):
                         cwd=tmp_path, check=True, capture_output=True, text=True)
     assert [l for l in r2.stdout.splitlines() if l.startswith("PSNR:")][0] == line
     assert not (tmp_path / "test_yuv.yuv").exists()
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[3], CASES[6], CASES[7]], ids=lambda c: f"{c['kind']}-q{c['qdc']}_{c['qac']}-ip{c['ip']}")
+def test_index_sidecar_gpu_bit_reader(tmp_path, case):
+    """icspenc --index writes <bin>.idx; icspdec finds it and parses on the GPU: same YUV as the reference
+    decoder (md5), same as the host-parser path (--no-index), also when the sequence is split into several device calls."""
+    n, qdc, qac, ip = case["nframes"], case["qdc"], case["qac"], case["ip"]
+    synth.make_clip(case["kind"], n, case["seed"]).tofile(tmp_path / "clip_cif.yuv")
+    env = dict(os.environ, ICSPENC_CALL_FRAMES=str(ip))          # one device call per GOP: the per-call indices are rebased
+    subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", str(ip), "--index", "--quiet"],
+                   cwd=tmp_path, check=True, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    binp = tmp_path / f"clip_compCIF_{qdc}_{qac}_{ip}.bin"
+    assert md5f(binp) == case["bin_md5"]
+    idx = np.fromfile(str(binp) + ".idx", np.uint8)
+    assert idx[:8].tobytes() == b"ICSPIDX1" and idx.size == 24 + 8 * n * 18
+    out = "check_test_intra_yuv.yuv" if ip == 1 else "check_test_inter_yuv.yuv"
+    r = subprocess.run([DEC, str(n), binp.name, str(qdc), str(qac), str(ip)], cwd=tmp_path, check=True, capture_output=True, text=True)
+    assert "bit reader on the GPU" in r.stderr
+    assert md5f(tmp_path / out) == case["dec_md5"]
+    os.remove(tmp_path / out)
+    r = subprocess.run([DEC, str(n), binp.name, str(qdc), str(qac), str(ip), "--no-index"], cwd=tmp_path, check=True, capture_output=True, text=True)
+    assert "bit reader on the host" in r.stderr
+    assert md5f(tmp_path / out) == case["dec_md5"]
