@@ -9,7 +9,18 @@ with IcspCuda(352, 288, max_frames=8) as ctx:
     res = ctx.encode_gops(frames, 2, 4, 8, 8)
     bodies, sbits, rec = ctx.encode_streams(frames, 2, 1, 4, 8, 8, want_recon=True)
     out = ctx.decode_gops(res.levels, res.mpm, res.ipm, res.mvd, 2, 4, 8, 8)
-    print("ok", int(sbits.sum()), out.shape)
+    sse = ctx.enc_sse(8)                                          # plane_sse_kernel
+    rows = ctx.bits_row_index(8)                                  # row_index_kernel
+    blob, offs, lens = bytearray(), [], []
+    for s in range(2):                                            # file bodies (reference tail rule), 4-byte aligned
+        nb = int(sbits[s]); b = bytearray(bytes(bodies[s]))
+        if nb % 8 == 0: b += b"\x00"
+        else: b[-1] = b[-1] >> (8 - nb % 8)
+        while len(blob) % 4: blob += b"\x00"
+        offs.append(len(blob)); lens.append(len(b)); blob += b
+    out2 = ctx.decode_streams(np.frombuffer(bytes(blob), np.uint8), offs, lens, rows, 2, 1, 4, 8, 8)   # parse_rows_kernel
+    assert np.array_equal(out, out2)
+    print("ok", int(sbits.sum()), out.shape, int(sse.sum()))
 with IcspCuda(64, 48, max_frames=4) as ctx:
     f = np.random.default_rng(0).integers(0, 255, size=(4, 64 * 48 * 3 // 2)).astype(np.uint8)
     r = ctx.encode_gops(f, 1, 4, 4, 4)
