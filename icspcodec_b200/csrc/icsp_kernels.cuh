@@ -374,19 +374,27 @@ __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtr
 // DECODE == 0: mode decision + coding + reconstruction (encoder table);
 // DECODE == 1: mode from (MPM, bit) + reconstruction with the decoder's binary64 table.
 // =====================================================================================================
-constexpr int IW_THREADS = 192;  // 24 block slots per wave step
-#ifndef IW_MIN_CTAS
-#define IW_MIN_CTAS 3
+#ifndef ICSP_IW_THREADS
+#define ICSP_IW_THREADS 96
 #endif
+constexpr int IW_THREADS = ICSP_IW_THREADS;  // 12 block slots per pass; 8 frames per SM (measured best of 64..192 threads)
+#ifndef IW_MIN_CTAS
+#define IW_MIN_CTAS 8
+#endif
+// Edge pixels are kept in place: block (bx, by) reads the bottom row of (bx, by-1) from bot[bx*8..] and the right column
+// of (bx-1, by) from right[by*8..], and overwrites exactly those slots with its own bottom row / right column when it is
+// done; nobody else needs the old values (the blocks of one wave have pairwise different bx and by, waves are separated
+// by __syncthreads).  One row + one column instead of a copy per block row / block column: 0.6 KB instead of 25 KB for
+// CIF, which is what lets 8 frames share an SM.
 struct IntraSmem {
-    uint8_t* bot;    // [bh][w]   bottom row of every block row
-    uint8_t* right;  // [bw][h]   right column of every block column
+    uint8_t* bot;    // [w]   bottom row of the block above, per column
+    uint8_t* right;  // [h]   right column of the block to the left, per row
     int* dc;         // [bh][bw]
     uint8_t* mode;   // [bh][bw]
 };
 __host__ __device__ inline size_t intra_smem_bytes(const Geom& g)
 {
-    return (size_t)g.bh * g.w + (size_t)g.bw * g.h + (size_t)g.bh * g.bw * 5 + 16;
+    return (size_t)g.w + (size_t)g.h + (size_t)g.bh * g.bw * 5 + 16;
 }
 
 // `edges` == nullptr: the edge/DC/mode maps live in dynamic shared memory (CIF .. 720x480); otherwise they live in a
@@ -401,8 +409,8 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
     IntraSmem sm;
     sm.dc = (int*)s_raw;
     sm.bot = s_raw + (size_t)g.bh * g.bw * 4;
-    sm.right = sm.bot + (size_t)g.bh * g.w;
-    sm.mode = sm.right + (size_t)g.bw * g.h;
+    sm.right = sm.bot + g.w;
+    sm.mode = sm.right + g.h;
     constexpr int TAB = DECODE ? 1 : 0;
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7, ngrp = IW_THREADS / 8;
     const int gop = blockIdx.x;
@@ -430,9 +438,9 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
             // neighbours from the reconstructed plane (shared-memory edges)
             int up[8], left_r, sumU = 0;
 #pragma unroll
-            for (int x = 0; x < 8; x++) { up[x] = hasU ? sm.bot[(byy - 1) * w + bx * 8 + x] : 128; sumU += up[x]; }
-            const int up_r = hasU ? sm.bot[(byy - 1) * w + bx * 8 + r] : 128;   // column r's own upper neighbour
-            left_r = hasL ? sm.right[(bx - 1) * g.h + byy * 8 + r] : 128;
+            for (int x = 0; x < 8; x++) { up[x] = hasU ? sm.bot[bx * 8 + x] : 128; sumU += up[x]; }
+            const int up_r = hasU ? sm.bot[bx * 8 + r] : 128;   // column r's own upper neighbour
+            left_r = hasL ? sm.right[byy * 8 + r] : 128;
             const int sumL = group_sum(left_r);
             // predVal = (predValLeft + predValUpper) / 16.0, a missing side contributes 128*8 (ENC:711-733)
             const double pd = __ddiv_rn((double)((hasL ? sumL : 1024) + (hasU ? sumU : 1024)), 16.0);
@@ -543,10 +551,10 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
             __syncwarp();
             if (active) {
                 *(uint2*)(recy + (size_t)(byy * 8 + r) * w + bx * 8) = *(const uint2*)(&px[8 * r]);
-                sm.bot[byy * w + bx * 8 + r] = out[7];
+                sm.bot[bx * 8 + r] = out[7];
                 if (r == 7) {
 #pragma unroll
-                    for (int y = 0; y < 8; y++) sm.right[bx * g.h + byy * 8 + y] = out[y];
+                    for (int y = 0; y < 8; y++) sm.right[byy * 8 + y] = out[y];
                 }
                 if (r == 0) sm.mode[byy * bw + bx] = (uint8_t)mode;
             }
