@@ -36,17 +36,18 @@ struct Pending { int k; cudaEvent_t a, b; };
 
 }  // namespace
 
+constexpr int MAX_CSTREAMS = 8;
 struct icsp_ctx {
     int device = 0;
     Geom g{};
     int cap = 0;  // frames
     cudaStream_t stream = nullptr;          // main stream: everything is ordered with respect to it
-    cudaStream_t cstream[4] = {};           // compute streams (GOP chunks round-robin: latency-bound kernels of one
+    cudaStream_t cstream[MAX_CSTREAMS] = {};           // compute streams (GOP chunks round-robin: latency-bound kernels of one
                                             // chunk overlap throughput-bound kernels of another)
     cudaStream_t s_up = nullptr, s_down = nullptr;   // H2D / D2H copy streams of the pipelined one-shot calls
-    cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
-    cudaStream_t hstream[4] = {};           // high-priority companions of cstream[] for the latency-bound kernels
-    cudaEvent_t ev_hi[4][2] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_CSTREAMS] = {};
+    cudaStream_t hstream[MAX_CSTREAMS] = {};           // high-priority companions of cstream[] for the latency-bound kernels
+    cudaEvent_t ev_hi[MAX_CSTREAMS][2] = {};
     bool hi_prio = true;
     std::vector<cudaEvent_t> ev_chunk;      // per-chunk upload / compute-done events
     int n_cstreams = 4;
@@ -274,7 +275,7 @@ cudaStream_t hi_begin(icsp_ctx* c, cudaStream_t s, int& idx)
 {
     idx = -1;
     if (!c->hi_prio) return s;
-    for (int i = 0; i < 4; i++) if (c->cstream[i] == s) idx = i;
+    for (int i = 0; i < MAX_CSTREAMS; i++) if (c->cstream[i] == s) idx = i;
     if (idx < 0) return s;
     if (cudaEventRecord(c->ev_hi[idx][0], s) != cudaSuccess || cudaStreamWaitEvent(c->hstream[idx], c->ev_hi[idx][0], 0) != cudaSuccess) { idx = -1; return s; }
     return c->hstream[idx];
@@ -426,7 +427,7 @@ int chunk_gops(const icsp_ctx* c, int n_gops, bool pipelined)
     const int min_chunk = 148;                       // one intra CTA per SM at least
     // resident runs: few large chunks (launch overhead, tails); pipelined host calls: more chunks so that the
     // first upload / last download are short (measured on B200: profiles/README.md)
-    int chunks = std::min(pipelined ? 8 : 4, std::max(1, n_gops / min_chunk));
+    int chunks = std::min(pipelined ? 8 : std::max(4, c->n_cstreams), std::max(1, n_gops / min_chunk));
     return (n_gops + chunks - 1) / chunks;
 }
 
@@ -481,13 +482,13 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, ICSP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? ICSP_ERR_NOMEM : ICSP_ERR_CUDA); } } while (0)
     CUB(cudaSetDevice(device));
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    if (const char* e = getenv("ICSP_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= 4) c->n_cstreams = v; }
+    if (const char* e = getenv("ICSP_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= MAX_CSTREAMS) c->n_cstreams = v; }
     if (const char* e = getenv("ICSP_CHUNK_GOPS")) { const int v = atoi(e); if (v >= 1) c->chunk_gops_target = v; }
-    for (int i = 0; i < 4; i++) CUB(cudaStreamCreateWithFlags(&c->cstream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < MAX_CSTREAMS; i++) CUB(cudaStreamCreateWithFlags(&c->cstream[i], cudaStreamNonBlocking));
     {
         int least = 0, greatest = 0;
         CUB(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < MAX_CSTREAMS; i++) {
             CUB(cudaStreamCreateWithPriority(&c->hstream[i], cudaStreamNonBlocking, greatest));
             for (auto& e : c->ev_hi[i]) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
@@ -496,7 +497,7 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     CUB(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    for (int i = 0; i < 4; i++) CUB(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    for (int i = 0; i < MAX_CSTREAMS; i++) CUB(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     const size_t F = (size_t)max_frames, nmb = (size_t)g.nmb;
     CUB(cudaMalloc(&c->d_cur, F * g.fb + 64));
     CUB(cudaMalloc(&c->d_rec, F * g.fb + 64));
@@ -1045,7 +1046,7 @@ uint64_t icsp_launch_count(const icsp_ctx* c) { return c ? c->launches : 0; }
 
 int icsp_configure(icsp_ctx* c, int n_compute_streams, int chunk_gops_)
 {
-    if (!c || n_compute_streams < 1 || n_compute_streams > 4 || chunk_gops_ < 0) return fail(c, ICSP_ERR_PARAM, "icsp_configure: bad arguments");
+    if (!c || n_compute_streams < 1 || n_compute_streams > MAX_CSTREAMS || chunk_gops_ < 0) return fail(c, ICSP_ERR_PARAM, "icsp_configure: bad arguments");
     c->n_cstreams = n_compute_streams;
     c->chunk_gops_target = chunk_gops_;
     return ICSP_OK;

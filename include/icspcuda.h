@@ -179,7 +179,7 @@ int icsp_set_profiling(icsp_ctx* ctx, int enabled);
 int icsp_reset_stats(icsp_ctx* ctx);
 int icsp_get_stats(icsp_ctx* ctx, icsp_kernel_stat* stats, int cap);   /* returns number of entries, syncs */
 uint64_t icsp_launch_count(const icsp_ctx* ctx);                       /* kernels launched since create/reset */
-/* Execution shape: number of compute streams the GOP chunks are spread over (1..4, default 4) and GOPs per chunk
+/* Execution shape: number of compute streams the GOP chunks are spread over (1..8, default 4) and GOPs per chunk
  * (0 = automatic).  n_streams = 1 with one chunk per call serialises every kernel on one stream, which is what the
  * per-kernel event timing wants. */
 int icsp_configure(icsp_ctx* ctx, int n_compute_streams, int chunk_gops);
