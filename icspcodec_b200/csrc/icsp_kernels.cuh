@@ -101,6 +101,7 @@ __device__ __forceinline__ MbBlock mb_block(const Geom& g, int mb, int mbx, int 
     return b;
 }
 
+
 __global__ void __launch_bounds__(TR_THREADS) fdct_quant_kernel(Geom g, FramePtrs p, Step st)
 {
     __shared__ double s_tile[TR_THREADS / 8][72];
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(TR_THREADS) idct_recon_kernel(Geom g, FramePtr
         const int dck = dc;
         __syncwarp();
         if (k + 1 < 6) fetch(k + 1, lv, pr, dc);           // next block's loads are in flight during this block's math
+        if (k + 2 < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(lvmb + (k + 2) * 64 + 8 * r));   // and the block after that is on its way to L2
         int q[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) q[u] = (int)s_lv[grp][iz_byte(izr, u)] * st.qac;   // IQuantization_block
@@ -809,7 +811,7 @@ __global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L
             me_task_store(L, s_win, s_cur0, task, band, me_task_load(g, refy, cury, task, band, 0, m0, nmbs, lane), nmbs, lane);
     __syncthreads();
 
-    const int mbl = warp;   // nwarps == nmbs
+    const int mbl = warp;   // nwarps == seg_mbs >= nmbs
     const uint32_t pk0 = __ldg(&g_slot[0][0][lane]), pk1 = __ldg(&g_slot[0][1][lane]);
     const int idx0 = pk0 & 255, dx0 = (int)(int8_t)(pk0 >> 8), dy0 = (int)(int8_t)(pk0 >> 16);
     const int idx1 = pk1 & 255, dx1 = (int)(int8_t)(pk1 >> 8), dy1 = (int)(int8_t)(pk1 >> 16);
@@ -826,7 +828,7 @@ __global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L
             pre1 = me_task_load(g, refy, cury, warp + nwarps, mby + 3, mby + 1, m0, nmbs, lane);
         }
         // (2) search macroblock (mby, m0 + mbl): both candidates of the lane share the current-row loads
-        {
+        if (mbl < nmbs) {   // the last segment of a frame can be one macroblock narrower than the CTA
             const uint4* crow = (const uint4*)(s_cur0 + (mby & 1) * cur_bytes + mbl * 16);
             // rows slot..slot+15 are contiguous thanks to the mirror
             const uint32_t* w0 = s_win + off0 + ((mby * 16 + 16 + dy0) & (ME_RING_ROWS - 1)) * pitch_w;

@@ -103,7 +103,7 @@ def test_gop_batch_equals_sequential(gpu, oracle):
         assert_syntax_equal(sub, s, what=f"gop {g}: ")
 
 
-@pytest.mark.parametrize("w,h", [(16, 16), (64, 48), (176, 144), (720, 480), (1280, 720), (1920, 1088)])
+@pytest.mark.parametrize("w,h", [(16, 16), (64, 48), (176, 144), (368, 48), (720, 480), (1280, 720), (1920, 1088)])   # 368 = 23 MBs: segments of 12 + 11
 def test_other_geometries(oracle, w, h):
     from icspcodec_b200 import IcspCuda
     rng = np.random.default_rng(w * 1000 + h)
