@@ -808,6 +808,12 @@ int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int g
     const int cs = chunk_streams(c, n_streams, gops_per_stream, true);
     const int nchunks = (n_streams + cs - 1) / cs;
     c->en_chunks.clear();
+    // ICSP_TIMELINE=1: print, per chunk, when its upload / kernels / downloads finished (ms from the start of the call);
+    // tools/e2e_timeline.py.  Shows the D2H link continuously busy from the end of the first chunk's kernels to the end.
+    static const bool timeline = getenv("ICSP_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> tl, tlb;
+    cudaEvent_t tl0 = nullptr;
+    if (timeline) { cudaEventCreate(&tl0); cudaEventRecord(tl0, c->stream); }
     CU(cudaEventRecord(c->ev_fork, c->stream));
     CU(cudaStreamWaitEvent(c->s_up, c->ev_fork, 0));
     for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
@@ -828,12 +834,19 @@ int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int g
         CU(cudaEventRecord(tbl, st));
         CU(cudaStreamWaitEvent(c->s_down, done, 0));
         if (out->recon) CU(cudaMemcpyAsync(out->recon + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, c->s_down));
+        if (timeline) {
+            cudaEvent_t e[3];
+            for (auto& x : e) cudaEventCreate(&x);
+            cudaEventRecord(e[0], c->s_up); cudaEventRecord(e[1], st); cudaEventRecord(e[2], c->s_down);
+            tl.insert(tl.end(), e, e + 3);
+        }
     }
     // pass 2: as each chunk's tables arrive, enqueue its body copy (overlaps the kernels of later chunks)
     size_t dst = 0;
     for (int i = 0; i < nchunks; i++) {
         CU(cudaEventSynchronize(chunk_event(c, 3 * i + 2)));
         if ((rc = body_to_host(c, i, out, dst, c->stream))) { cudaDeviceSynchronize(); return rc; }   // main stream is idle: bodies do not queue behind recon copies
+        if (timeline) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); tlb.push_back(e); }
     }
     if ((rc = join_streams(c))) return rc;
     CU(cudaEventRecord(c->ev_join[0], c->s_down));
@@ -841,7 +854,23 @@ int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int g
     CU(cudaEventRecord(c->ev_join[1], c->s_up));
     CU(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
     CU(cudaGetLastError());
-    return icsp_sync(c);
+    rc = icsp_sync(c);
+    if (timeline) {
+        cudaEvent_t end; cudaEventCreate(&end); cudaEventRecord(end, c->stream); cudaEventSynchronize(end);
+        float t;
+        for (int i = 0; i < nchunks; i++) {
+            float a, b, d, e;
+            cudaEventElapsedTime(&a, tl0, tl[3 * i]); cudaEventElapsedTime(&b, tl0, tl[3 * i + 1]); cudaEventElapsedTime(&d, tl0, tl[3 * i + 2]);
+            cudaEventElapsedTime(&e, tl0, tlb[i]);
+            fprintf(stderr, "[icsp timeline] chunk %d: upload done %.1f ms, kernels done %.1f ms, recon download done %.1f ms, body download done %.1f ms\n", i, a, b, d, e);
+        }
+        cudaEventElapsedTime(&t, tl0, end);
+        fprintf(stderr, "[icsp timeline] call done %.1f ms\n", t);
+        for (auto e : tl) cudaEventDestroy(e);
+        for (auto e : tlb) cudaEventDestroy(e);
+        cudaEventDestroy(tl0); cudaEventDestroy(end);
+    }
+    return rc;
 }
 
 // macroblock-row index of what icsp_encode_streams / icsp_entropy_run just coded (SURVEY.md §8 f3 side-car)
