@@ -258,7 +258,7 @@ def ours(args) -> dict | None:
     batch = make_batch(args.streams, args.frames, rank)[:n]
     ctx = IcspCuda(W, H, max_frames=n, device=local)
     from icspcodec_b200 import PinnedArray
-    pin_in = PinnedArray((n, FB), np.uint8)
+    pin_in = PinnedArray((n, FB), np.uint8, upload_only=True)   # write-combined: the CPU only fills it, the GPU reads it
     pin_in.array[:] = batch
     del batch
     res = ctx.alloc_result(n, pinned=True)

@@ -40,7 +40,7 @@ EXPORTS = [
     "icsp_me_sad", "icsp_dct8x8", "icsp_idct8x8",
     "icsp_set_profiling", "icsp_reset_stats", "icsp_get_stats", "icsp_launch_count",
     "icsp_event_record", "icsp_event_elapsed_ms",
-    "icsp_host_alloc", "icsp_host_free",
+    "icsp_host_alloc", "icsp_host_alloc_upload", "icsp_host_free",
     "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body", "icsp_bits_bound", "icsp_enc_sse", "icsp_bits_row_index", "icsp_decode_streams",
 ]
 
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     lib.icsp_bits_bound.restype = C.c_size_t
     lib.icsp_host_alloc.argtypes = [C.c_size_t]
     lib.icsp_host_alloc.restype = vp
+    lib.icsp_host_alloc_upload.argtypes = [C.c_size_t]
+    lib.icsp_host_alloc_upload.restype = vp
     lib.icsp_host_free.argtypes = [vp]
     lib.icsp_host_free.restype = None
     _lib = lib

@@ -36,10 +36,11 @@ def _ptr(a: np.ndarray | None):
 class PinnedArray:
     """numpy view over cudaHostAlloc'd memory (kept alive by this object)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, upload_only: bool = False):
+        """upload_only: write-combined memory (icsp_host_alloc_upload) for buffers the CPU only writes."""
         self._lib = _lib.load()
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        self._p = self._lib.icsp_host_alloc(max(nbytes, 1))
+        self._p = (self._lib.icsp_host_alloc_upload if upload_only else self._lib.icsp_host_alloc)(max(nbytes, 1))
         if not self._p:
             raise IcspError("icsp_host_alloc failed")
         buf = (C.c_char * max(nbytes, 1)).from_address(self._p)

@@ -595,6 +595,13 @@ void* icsp_host_alloc(size_t bytes)
     if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
     return p;
 }
+void* icsp_host_alloc_upload(size_t bytes)
+{   // write-combined: not snooped during the transfer (several GPUs uploading at once no longer contend in the host's
+    // coherence fabric: 4-GPU e2e 333 k -> measured below in profiles/README.md); CPU reads of it are very slow
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) return nullptr;
+    return p;
+}
 void icsp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int icsp_sync(icsp_ctx* c)

@@ -104,7 +104,7 @@ int main(int argc, char** argv)
 
     FILE* fi = fopen(o.input.c_str(), "rb");
     if (!fi) { fprintf(stderr, "[ERROR] cannot open %s\n", o.input.c_str()); return 1; }
-    uint8_t* frames = (uint8_t*)icsp_host_alloc((size_t)n * fb);
+    uint8_t* frames = (uint8_t*)icsp_host_alloc_upload((size_t)n * fb);   // the CPU only writes it (fread), the GPUs read it
     if (!frames) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host, %zu bytes); is a CUDA device present? libicspcuda has no CPU fallback\n", (size_t)n * fb); return 1; }
     if (fread(frames, fb, n, fi) != (size_t)n) { fprintf(stderr, "[ERROR] %s holds fewer than %d frames of %dx%d\n", o.input.c_str(), n, o.width, o.height); return 1; }
     fclose(fi);

@@ -80,6 +80,10 @@ int icsp_sync(icsp_ctx* ctx);
 /* Page-locked host memory for the SoA arrays / frames (fast, truly asynchronous H2D/D2H). Plain malloc'd
  * buffers are accepted everywhere too; they are just slower to copy. */
 void* icsp_host_alloc(size_t bytes);
+/* The same, write-combined: for buffers the CPU only WRITES (frames read from a file, then uploaded).  The device reads
+ * them without snooping the CPU caches, which matters when several GPUs upload at once; reading them back on the CPU is
+ * very slow, so never use it for outputs.  Freed with icsp_host_free. */
+void* icsp_host_alloc_upload(size_t bytes);
 void icsp_host_free(void* p);
 
 /* ---- encoder: replaces intraPrediction / interPrediction over a batch of closed GOPs -------------- */
