@@ -158,7 +158,7 @@ struct BitReader {
         int e, prefix;
         if (top3 != 7) { e = (int)top3 - 2; prefix = 3; }
         else {
-            const int ones = __builtin_clzll(~w);                               // >= 3
+            const int ones = ~w ? __builtin_clzll(~w) : 64;                     // >= 3 (clz(0) is undefined)
             if (ones >= 10) return 0;              // no category matches: the reference leaves len = 0, val = 0
             e = ones + 2; prefix = ones + 1;
         }
