@@ -81,10 +81,11 @@ static inline void put_block(BitString& bs, const int16_t* zz, int acflag)
     else for (int k = 1; k < 64; k++) put_vlc(bs, zz[k]);
 }
 
-void encode_frame(BitString& bs, const Syntax& s, int frame, int nmb, bool intra)
+void encode_frame(BitString& bs, const Syntax& s, int frame, int nmb, bool intra, int mbw, uint64_t* row_bits)
 {
     for (int mb = 0; mb < nmb; mb++) {
         const size_t m = (size_t)frame * nmb + mb;
+        if (row_bits && mbw > 0 && mb % mbw == 0) row_bits[mb / mbw] = bs.size_bits();   // bit offset of this MB row inside the frame
         if (!intra) {
             bs.put(1, 1);                                              // mv mode flag (ENC:5151)
             put_vlc(bs, s.mvd[m * 2]);
@@ -110,15 +111,16 @@ std::vector<uint8_t> stream_header(const StreamParams& p)
     return out;
 }
 
-std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_threads)
+std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_threads, std::vector<uint64_t>* row_index)
 {
-    const int nmb = (p.width / 16) * (p.height / 16);
+    const int nmb = (p.width / 16) * (p.height / 16), mbw = p.width / 16, mbh = p.height / 16;
     std::vector<BitString> per_frame((size_t)p.nframes);
+    if (row_index) row_index->assign((size_t)p.nframes * mbh, 0);
     n_threads = std::max(1, std::min(n_threads, p.nframes));
     auto work = [&](int tid) {
         for (int n = tid; n < p.nframes; n += n_threads) {
             const bool intra = p.intra_period == 0 || n % p.intra_period == 0;
-            encode_frame(per_frame[n], s, n, nmb, intra);
+            encode_frame(per_frame[n], s, n, nmb, intra, mbw, row_index ? row_index->data() + (size_t)n * mbh : nullptr);
         }
     };
     std::vector<std::thread> th;
@@ -126,7 +128,10 @@ std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_
     work(0);
     for (auto& t : th) t.join();
     BitString all;
-    for (auto& f : per_frame) all.append(f);
+    for (size_t n = 0; n < per_frame.size(); n++) {
+        if (row_index) for (int y = 0; y < mbh; y++) (*row_index)[n * mbh + y] += all.size_bits();   // frame offset inside the body
+        all.append(per_frame[n]);
+    }
 
     std::vector<uint8_t> out = stream_header(p);
     const std::vector<uint8_t> body = all.reference_body();
@@ -180,7 +185,7 @@ struct BitReader {
 };
 }  // namespace
 
-ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes)
+ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes, const std::vector<uint64_t>* row_index)
 {
     if (file.size() < 14) throw std::runtime_error("bitstream shorter than its 14-byte header");
     ParsedStream ps;
@@ -199,10 +204,14 @@ ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes)
     std::vector<uint8_t> padded(file.size() - 14 + 16, 0);              // the reader loads 8 bytes at a time
     memcpy(padded.data(), file.data() + 14, file.size() - 14);
     BitReader r{padded.data(), (uint64_t)(file.size() - 14) * 8};
+    const int mbw = ps.p.width / 16, mbh = ps.p.height / 16;
+    if (row_index && row_index->size() < (size_t)nframes * mbh) throw std::runtime_error("row index shorter than nframes x macroblock rows");
     for (int n = 0; n < nframes; n++) {
         const bool intra = ps.p.intra_period == 1 || n % ps.p.intra_period == 0;   // DEC:98, DEC:201
         for (int mb = 0; mb < nmb; mb++) {
             const size_t m = (size_t)n * nmb + mb;
+            // with an index every macroblock row starts from its recorded offset (the chain the GPU bit reader follows)
+            if (row_index && mb % mbw == 0) r.pos = (*row_index)[(size_t)n * mbh + mb / mbw];
             if (!intra) {
                 (void)r.get();                                          // MVmodeflag (DEC:301)
                 ps.mvd[m * 2] = (int16_t)r.vlc();

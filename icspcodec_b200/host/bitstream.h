@@ -47,13 +47,15 @@ private:
 void put_vlc(BitString& bs, int v);
 
 // one frame (intra: MPM/mode bits + 6 blocks per MB; inter: mv flag + MVD + 6 blocks per MB)
-void encode_frame(BitString& bs, const Syntax& s, int frame, int nmb, bool intra);
+// row_bits (optional, [height/16]): bit offset of every macroblock row inside the frame's bit string (mbw = width/16)
+void encode_frame(BitString& bs, const Syntax& s, int frame, int nmb, bool intra, int mbw = 0, uint64_t* row_bits = nullptr);
 
 // 14-byte header (ENC.h:201-212 packed, ENC:4901-4922)
 std::vector<uint8_t> stream_header(const StreamParams& p);
 
 // whole stream; frames are entropy coded in parallel (n_threads) and merged in order
-std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_threads);
+// row_index (optional): [nframes][height/16] bit offsets from the body start, the side-car of icspenc --index / icsp_bits_row_index
+std::vector<uint8_t> write_stream(const StreamParams& p, const Syntax& s, int n_threads, std::vector<uint64_t>* row_index = nullptr);
 
 // ---- reader ----------------------------------------------------------------------------------------
 struct ParsedStream {
@@ -63,6 +65,8 @@ struct ParsedStream {
     std::vector<int16_t> mvd;
 };
 // Parses header + body MSB-first, every byte including the last one (DEC:60-74).  Throws std::runtime_error.
-ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes);
+// row_index (optional): restart every macroblock row at its recorded bit offset — the chains the GPU bit reader
+// (parse_rows_kernel) follows, on the host; with a correct index the result equals the serial parse.
+ParsedStream parse_stream(const std::vector<uint8_t>& file, int nframes, const std::vector<uint64_t>* row_index = nullptr);
 
 }  // namespace icsp_host

@@ -94,7 +94,6 @@ int main(int argc, char** argv)
         fprintf(stderr, "[ERROR] uncorrect parameters (need -i, -n > 0, QP in 1..255, intraPeriod in 0..63, width/height multiples of 16)\n");
         return 1;
     }
-    if (o.index && o.host_entropy) { fprintf(stderr, "[ERROR] --index needs the GPU entropy coder (drop --host-entropy)\n"); return 1; }
     const size_t us = o.input.find('_');
     if (us == std::string::npos) { fprintf(stderr, "[ERROR] input file name must contain '_' (encoder_main.cpp:13)\n"); return 1; }
     const std::string slash_stripped = o.input.substr(0, us);
@@ -191,13 +190,26 @@ int main(int argc, char** argv)
     if (!o.quiet)
         for (int f = 0; f < n; f++) printf("Encoding FRAME_%03d(%c) done!\n", f, (o.ip == 0 || f % o.ip == 0) ? 'I' : 'P');
 
+    // side-car: "ICSPIDX1", width, height, frames, macroblock rows (u32 LE), then u64 LE bit offsets from the body start
+    auto write_index = [&](const std::vector<uint64_t>& index) {
+        char iname[520];
+        snprintf(iname, sizeof(iname), "%s_compCIF_%d_%d_%d.bin.idx", slash_stripped.c_str(), o.qdc, o.qac, o.ip);
+        FILE* fx = fopen(iname, "wb");
+        if (!fx) { fprintf(stderr, "fail to open %s\n", iname); return false; }
+        const uint32_t hdr[4] = {(uint32_t)o.width, (uint32_t)o.height, (uint32_t)n, (uint32_t)(o.height / 16)};
+        fwrite("ICSPIDX1", 1, 8, fx); fwrite(hdr, 4, 4, fx); fwrite(index.data(), 8, index.size(), fx);
+        fclose(fx);
+        return true;
+    };
     icsp_host::StreamParams sp;
     sp.width = o.width; sp.height = o.height; sp.qp_dc = o.qdc; sp.qp_ac = o.qac; sp.intra_period = o.ip; sp.nframes = n;
     std::vector<uint8_t> bin;
     if (o.host_entropy) {
         icsp_host::Syntax syn{levels, acflag, mpm, ipm, mvd};
         const int hw = (int)std::thread::hardware_concurrency();
-        bin = icsp_host::write_stream(sp, syn, o.threads > 0 ? o.threads : std::max(1, hw));
+        std::vector<uint64_t> index;
+        bin = icsp_host::write_stream(sp, syn, o.threads > 0 ? o.threads : std::max(1, hw), o.index ? &index : nullptr);
+        if (o.index && !write_index(index)) return 1;
     } else {   // concatenate the per-shard bit strings in frame order (frames are not byte aligned in the stream, H7)
         std::sort(shards.begin(), shards.end(), [](const Shard& a, const Shard& b) { return a.first_frame < b.first_frame; });
         icsp_host::BitString all;
@@ -209,15 +221,7 @@ int main(int argc, char** argv)
                 if (o.index) for (uint64_t r : s.rows[i]) index.push_back(base + r);
                 base += s.bits[i].second;
             }
-        if (o.index) {   // side-car: "ICSPIDX1", width, height, frames, macroblock rows (u32 LE), then u64 LE bit offsets from the body start
-            char iname[520];
-            snprintf(iname, sizeof(iname), "%s_compCIF_%d_%d_%d.bin.idx", slash_stripped.c_str(), o.qdc, o.qac, o.ip);
-            FILE* fx = fopen(iname, "wb");
-            if (!fx) { fprintf(stderr, "fail to open %s\n", iname); return 1; }
-            const uint32_t hdr[4] = {(uint32_t)o.width, (uint32_t)o.height, (uint32_t)n, (uint32_t)(o.height / 16)};
-            fwrite("ICSPIDX1", 1, 8, fx); fwrite(hdr, 4, 4, fx); fwrite(index.data(), 8, index.size(), fx);
-            fclose(fx);
-        }
+        if (o.index && !write_index(index)) return 1;
         bin = icsp_host::stream_header(sp);
         const std::vector<uint8_t> body = all.reference_body();
         bin.insert(bin.end(), body.begin(), body.end());

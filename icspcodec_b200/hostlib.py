@@ -18,6 +18,7 @@ def load() -> C.CDLL:
             raise RuntimeError(f"{p} missing: run `python -m icspcodec_b200.build`")
         _LIB = C.CDLL(p)
         _LIB.icsp_host_write_stream.restype = C.c_long
+        _LIB.icsp_host_write_stream_indexed.restype = C.c_long
     return _LIB
 
 
@@ -52,4 +53,39 @@ def parse_stream(data: bytes, nframes: int):
     rc = load().icsp_host_parse_stream(_p(arr), C.c_long(len(data)), nframes, hdr, _p(levels), _p(acflag), _p(mpm), _p(ipm), _p(mvd))
     if rc != 0:
         raise ValueError("stream parse failed")
+    return dict(levels=levels, acflag=acflag, mpm=mpm, ipm=ipm, mvd=mvd), dict(w=w, h=h, qdc=qdc, qac=qac, ip=ip)
+
+
+def write_stream_indexed(levels, acflag, mpm, ipm, mvd, w: int, h: int, qdc: int, qac: int, ip: int, threads: int = 4):
+    """-> (file bytes, rows[n][h/16] uint64): the stream plus the bit offset of every macroblock row from the body start."""
+    n = levels.shape[0]
+    cap = 64 + n * (w // 16) * (h // 16) * 800
+    out = np.zeros(cap, np.uint8)
+    rows = np.zeros((n, h // 16), np.uint64)
+    arrs = [np.ascontiguousarray(levels, np.int16), np.ascontiguousarray(acflag, np.uint8), np.ascontiguousarray(mpm, np.uint8),
+            np.ascontiguousarray(ipm, np.uint8), np.ascontiguousarray(mvd, np.int16)]
+    ln = load().icsp_host_write_stream_indexed(*[_p(a) for a in arrs], n, w, h, qdc, qac, ip, threads, _p(out), C.c_long(cap), _p(rows))
+    if ln < 0:
+        raise ValueError("icsp_host_write_stream_indexed failed")
+    return out[:ln].tobytes(), rows
+
+
+def parse_stream_indexed(data: bytes, nframes: int, rows: np.ndarray):
+    """Parse with every macroblock row restarted at its recorded bit offset (the chains of the GPU bit reader)."""
+    arr = np.frombuffer(data, np.uint8)
+    hdr = (C.c_int * 5)()
+    if load().icsp_host_parse_stream(_p(arr), C.c_long(len(data)), 0, hdr, None, None, None, None, None) != 0:
+        raise ValueError("bad stream header")
+    w, h, qdc, qac, ip = list(hdr)
+    nmb = (w // 16) * (h // 16)
+    levels = np.zeros((nframes, nmb, 6, 64), np.int16)
+    acflag = np.zeros((nframes, nmb, 6), np.uint8)
+    mpm = np.zeros((nframes, nmb, 4), np.uint8)
+    ipm = np.zeros((nframes, nmb, 4), np.uint8)
+    mvd = np.zeros((nframes, nmb, 2), np.int16)
+    rows = np.ascontiguousarray(rows, np.uint64)
+    rc = load().icsp_host_parse_stream_indexed(_p(arr), C.c_long(len(data)), nframes, _p(rows), C.c_long(rows.size), _p(levels), _p(acflag),
+                                               _p(mpm), _p(ipm), _p(mvd))
+    if rc != 0:
+        raise ValueError("indexed stream parse failed")
     return dict(levels=levels, acflag=acflag, mpm=mpm, ipm=ipm, mvd=mvd), dict(w=w, h=h, qdc=qdc, qac=qac, ip=ip)

@@ -147,3 +147,9 @@ def test_index_sidecar_gpu_bit_reader(tmp_path, case):
     r = subprocess.run([DEC, str(n), binp.name, str(qdc), str(qac), str(ip), "--no-index"], cwd=tmp_path, check=True, capture_output=True, text=True)
     assert "bit reader on the host" in r.stderr
     assert md5f(tmp_path / out) == case["dec_md5"]
+    # the host entropy coder writes the same side-car
+    idx_gpu = md5f(str(binp) + ".idx")
+    os.remove(str(binp) + ".idx")
+    subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", str(ip), "--index", "--host-entropy", "--quiet"],
+                   cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert md5f(binp) == case["bin_md5"] and md5f(str(binp) + ".idx") == idx_gpu

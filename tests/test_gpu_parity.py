@@ -335,6 +335,11 @@ def test_gpu_bit_reader_matches_reference_decoder(gpu, case):
     assert rows.shape == (case["nframes"], H // 16) and rows[0, 0] == 0 and np.all(np.diff(rows.reshape(-1).astype(np.int64)) > 0)
     out = gpu.decode_sequence_bitstream(data, rows, case["nframes"])
     assert hashlib.md5(out.tobytes()).hexdigest() == case["dec_md5"]
+    # the index exported from the GPU's prefix sums is the one the host writer computes for the same syntax
+    from icspcodec_b200 import hostlib
+    res = gpu.encode_sequence(clip, case["qdc"], case["qac"], case["ip"])
+    data_h, rows_h = hostlib.write_stream_indexed(res.levels, res.acflag, res.mpm, res.ipm, res.mvd, W, H, case["qdc"], case["qac"], case["ip"])
+    assert data_h == data and np.array_equal(rows_h, rows)
 
 
 def test_gpu_bit_reader_stream_batch(oracle):

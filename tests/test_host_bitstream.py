@@ -72,3 +72,25 @@ def test_empty_and_bad_streams(host):
     hdr0 = bytes([0, 73, 67, 83, 80, 32, 1, 96, 1, 8, 8, 0, 0, 0]) + b"\x00" * 64
     with pytest.raises(ValueError):
         host.parse_stream(hdr0, 1)
+
+
+def test_row_index_roundtrip(oracle):
+    """Macroblock-row index (SURVEY §8 f3 side-car): the host writer's offsets let every macroblock row be parsed on its own
+    (parse_stream_indexed = the chains the GPU bit reader follows) with the same result as the serial parse; offsets ascend,
+    start at 0, and the stream bytes equal the un-indexed writer's."""
+    from icspcodec_b200 import hostlib, synth
+    for kind, n, qdc, qac, ip in (("akiyo", 5, 8, 8, 3), ("highmotion", 4, 1, 16, 2), ("intra", 3, 8, 8, 1), ("flat", 4, 16, 16, 4)):
+        clip = synth.make_clip(kind, n, 5)
+        s = oracle.encode(clip, 352, 288, qdc, qac, ip)
+        data, rows = hostlib.write_stream_indexed(s.levels, s.acflag, s.mpm, s.ipm, s.mvd, 352, 288, qdc, qac, ip, threads=3)
+        assert data == oracle.write_bitstream(s, 352, 288, qdc, qac, ip)
+        flat = rows.reshape(-1).astype(np.int64)
+        assert rows.shape == (n, 18) and flat[0] == 0 and np.all(np.diff(flat) > 0) and flat[-1] < (len(data) - 14) * 8
+        serial, _ = hostlib.parse_stream(data, n)
+        indexed, _ = hostlib.parse_stream_indexed(data, n, rows)
+        for k in serial:
+            assert np.array_equal(serial[k], indexed[k]), k
+        # a shifted index must change the result (the index is really used)
+        bad = rows.copy(); bad[1:, :] += np.uint64(1)
+        wrong, _ = hostlib.parse_stream_indexed(data, n, bad)
+        assert not np.array_equal(wrong["levels"], serial["levels"])
