@@ -126,14 +126,14 @@ int icsp_encode_streams(icsp_ctx* ctx, const uint8_t* i420_frames, int n_streams
  * icsp_bits_download. */
 int icsp_entropy_run(icsp_ctx* ctx, int n_streams, int gops_per_stream, int gop_len);
 int icsp_bits_download(icsp_ctx* ctx, int n_streams, const icsp_bits_out* out);   /* synchronous */
-/* In place: turns an MSB-first body of nbits bits (buffer must hold nbits/8+1 bytes) into the reference's file body;
- * returns its length nbits/8+1. */
 /* Macroblock-row index of what icsp_encode_streams / icsp_entropy_run just coded: rows[f*(height/16) + y]
  * = bit offset, from the start of its stream's body, of the first macroblock of row y of frame f (f < n_frames, frames in
  * the order of the call).  8 bytes per row (0.4 % of a CIF stream); icspenc --index stores it as "<bin>.idx".  The stream
  * format has no resynchronisation points (DEC:38-404 is one serial VLC chain); with this index every macroblock row is an
  * independent chain and icsp_decode_streams parses on the GPU.  Synchronous. */
 int icsp_bits_row_index(icsp_ctx* ctx, int n_frames, uint64_t* rows);
+/* In place: turns an MSB-first body of nbits bits (buffer must hold nbits/8+1 bytes) into the reference's file body;
+ * returns its length nbits/8+1. */
 size_t icsp_finish_body(uint8_t* body, uint64_t nbits);
 /* worst-case size in bytes of the packed bodies of n_frames frames (any content, any QP), incl. alignment slack */
 size_t icsp_bits_bound(int width, int height, int n_frames);
@@ -173,7 +173,7 @@ int icsp_idct8x8(icsp_ctx* ctx, const int32_t* blocks, int n, int table, double*
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* When enabled every kernel launch is bracketed by CUDA events on the context stream. */
-#define ICSP_MAX_KERNELS 24
+#define ICSP_MAX_KERNELS 32
 typedef struct icsp_kernel_stat {
     char name[40];
     uint64_t launches;
