@@ -143,6 +143,8 @@ int main(int argc, char** argv)
         icsp_ctx* ctx = nullptr;
         s.rc = icsp_create(&ctx, s.device, o.width, o.height, per_call_gops * s.gop_len);
         if (s.rc) { s.err = icsp_last_error(nullptr); return; }
+        uint8_t* stage = nullptr;
+        size_t stage_cap = 0;
         for (int g = 0; g < s.n_gops && !s.rc; g += per_call_gops) {
             const int ng = std::min(per_call_gops, s.n_gops - g);
             const size_t f0 = (size_t)s.first_frame + (size_t)g * s.gop_len;
@@ -151,21 +153,33 @@ int main(int argc, char** argv)
                                  mvd + f0 * nmb * 2, nullptr, nullptr, recon ? recon + f0 * fb : nullptr};
                 s.rc = icsp_encode_gops(ctx, frames + f0 * fb, ng, s.gop_len, o.qdc, o.qac, &out);
             } else {   // entropy coding + bit packing on the GPU: only bits (and the reconstruction) cross PCIe
-                const size_t cap = icsp_bits_bound(o.width, o.height, ng * s.gop_len);
-                std::vector<uint8_t> buf(cap);
+                // pinned staging buffer, reused by the shard's calls.  First sized like the reference's own buffer (width*height
+                // bytes per frame, ENC:4874: plenty for natural content); a call that does not fit is repeated with the worst-case bound
+                const size_t cnt_frames = (size_t)ng * s.gop_len;
+                size_t cap = cnt_frames * ((size_t)o.width * o.height + 32) + 64;
                 uint64_t nbits = 0, off = 0;
-                icsp_bits_out bo{buf.data(), cap, &nbits, &off, recon ? recon + f0 * fb : nullptr};
-                s.rc = icsp_encode_streams(ctx, frames + f0 * fb, 1, ng, s.gop_len, o.qdc, o.qac, &bo);
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    if (stage_cap < cap) {
+                        icsp_host_free(stage);
+                        stage = (uint8_t*)icsp_host_alloc(cap);
+                        stage_cap = stage ? cap : 0;
+                        if (!stage) { s.rc = ICSP_ERR_NOMEM; s.err = "pinned staging buffer for the bitstream"; break; }
+                    }
+                    icsp_bits_out bo{stage, stage_cap, &nbits, &off, recon ? recon + f0 * fb : nullptr};
+                    s.rc = icsp_encode_streams(ctx, frames + f0 * fb, 1, ng, s.gop_len, o.qdc, o.qac, &bo);
+                    if (s.rc != ICSP_ERR_CAPACITY) break;
+                    cap = icsp_bits_bound(o.width, o.height, (int)cnt_frames);
+                    if (stage_cap >= cap) break;             // already at the bound: a real capacity error
+                }
+                if (s.rc == ICSP_ERR_NOMEM) break;
+                std::vector<uint8_t> buf;
+                if (!s.rc) buf.assign(stage + off, stage + off + (size_t)((nbits + 7) / 8));
                 if (!s.rc && o.index) {
                     std::vector<uint64_t> r((size_t)ng * s.gop_len * (o.height / 16));
                     s.rc = icsp_bits_row_index(ctx, ng * s.gop_len, r.data());
                     s.rows.push_back(std::move(r));
                 }
-                if (!s.rc) {
-                    buf.erase(buf.begin(), buf.begin() + (long)off);
-                    buf.resize((size_t)((nbits + 7) / 8));
-                    s.bits.emplace_back(std::move(buf), nbits);
-                }
+                if (!s.rc) s.bits.emplace_back(std::move(buf), nbits);
             }
             if (!s.rc && o.psnr) {   // the frames and their reconstruction are still resident
                 const size_t at = s.sse.size();
@@ -175,6 +189,7 @@ int main(int argc, char** argv)
             if (s.rc) s.err = icsp_last_error(ctx);
         }
         (void)cnt;
+        icsp_host_free(stage);
         icsp_destroy(ctx);
     };
     {

@@ -153,3 +153,19 @@ def test_index_sidecar_gpu_bit_reader(tmp_path, case):
     subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", str(ip), "--index", "--host-entropy", "--quiet"],
                    cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert md5f(binp) == case["bin_md5"] and md5f(str(binp) + ".idx") == idx_gpu
+
+
+def test_icspenc_noise_at_qp1_exceeds_reference_buffer(tmp_path, oracle):
+    """Random noise at QP 1 codes to more than width*height bytes per frame — the reference overruns its own buffer there
+    (ENC:4874); icspenc retries the call with the worst-case staging buffer and still matches the oracle bit for bit."""
+    w, h, n = 64, 48, 3
+    rng = np.random.default_rng(99)
+    clip = rng.integers(0, 256, size=(n, w * h * 3 // 2)).astype(np.uint8)
+    clip.tofile(tmp_path / "noise_x.yuv")
+    subprocess.run([ENC, "-i", "noise_x.yuv", "-w", str(w), "-h", str(h), "-n", str(n), "-q", "1", "--intraPeriod", "2", "--quiet"],
+                   cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    s = oracle.encode(clip, w, h, 1, 1, 2)
+    want = oracle.write_bitstream(s, w, h, 1, 1, 2)
+    assert len(want) > n * w * h                                   # the case really is beyond the reference's bound
+    assert open(tmp_path / "noise_compCIF_1_1_2.bin", "rb").read() == want
+    assert np.array_equal(np.fromfile(tmp_path / "test_yuv.yuv", np.uint8).reshape(n, -1), s.recon.reshape(n, -1))
