@@ -18,6 +18,10 @@ struct Geom {
     int bw, bh;    // luma 8x8 grid
     int fb;        // bytes per I420 frame
     unsigned magic_bw, magic_mbw;  // ceil(2^32/bw), ceil(2^32/mbw): n/d == umulhi(n, magic) while n*d < 2^32
+    unsigned magic_mbw2;           // ceil(2^32/(mbw-2)) (interior macroblocks per row), 0 if mbw <= 2
+    // block k of a macroblock (Y0..Y3, Cb, Cr) relative to block 0 of its plane group (luma: Y0, chroma: Cb):
+    int d_pix[6];                  // byte offset inside a frame: luma (k>>1)*8*w + (k&1)*8; Cb 0, Cr cw*ch
+    int d_dc[6];                   // index into the plane-raster DC maps: luma (k>>1)*bw + (k&1); Cb 4*nmb, Cr 5*nmb
 };
 
 __constant__ signed char c_cand[8][64][2];  // spiral visiting order per carried start state: (dx,dy) (ENC:2101-2143)

@@ -16,12 +16,13 @@ struct FramePtrs {
     int16_t* mvd;        // [F][nmb][2]
     int16_t* mv;         // [F][nmb][2]
     int32_t* minsad;     // [F][nmb]
-    double* dcraw;       // [G][6*nmb] scaled forward-DCT DC, plane-raster order: Y[bh][bw], Cb[mbh][mbw], Cr
-    int32_t* dcrec;      // [G][6*nmb] reconstructed DC, same order
+    double* dcraw;       // [G][nmb][6] scaled forward-DCT DC, macroblock major like the levels (Y0..Y3, Cb, Cr)
+    int32_t* dcrec;      // [G][nmb][6] reconstructed DC, same order
     uint8_t* mestate;    // [G][nmb]  spiral start state per macroblock
     uint8_t* memoves;    // [G][nmb]  moves made by the search (64 = no early break)
     uint32_t* meflag;    // [G]       number of macroblocks of the frame whose search broke early
     unsigned long long* mezero;  // [G][nmb][8] zero-SAD masks per start state (exact fallback only)
+    double* dct_tap;     // optional debug tap [F][nmb][6][64]: forward DCT output, raster order, before the DC predictor (NULL = off)
 };
 
 struct Step {
@@ -29,6 +30,7 @@ struct Step {
     int qdc, qac;
     int intra;       // 1: intra frame (transform kernels touch chroma only; luma is the wavefront kernel)
     unsigned magic_ac, magic_dc;  // ceil(2^31/q), see div_magic
+    int qmode_ac, m19_ac;         // qmode_ac == 0: AC levels by div_m19 with m19_ac = floor(2^19/qac)+1 (qac <= 128); 1: div_magic
 };
 
 // item -> (mb, k, plane geometry)
@@ -37,7 +39,7 @@ struct BlockId {
     int bx, by;        // position in the plane's 8x8 grid
     int pw, ph;        // plane size
     int poff;          // plane offset inside a frame
-    int dcidx;         // index into dcraw/dcrec (plane-raster order)
+    int dcidx;         // index into dcraw/dcrec (macroblock major)
 };
 // luma launches: item = mb*4 + k ; chroma launches: item = mb*2 + (k-4)
 template <bool CHROMA>
@@ -49,11 +51,11 @@ __device__ __forceinline__ BlockId block_id(const Geom& g, int item)
     const int mby = (int)__umulhi((unsigned)b.mb, g.magic_mbw), mbx = b.mb - mby * g.mbw;
     if (!CHROMA) {
         b.plane = 0; b.bx = 2 * mbx + (b.k & 1); b.by = 2 * mby + (b.k >> 1);
-        b.pw = g.w; b.ph = g.h; b.poff = 0; b.dcidx = b.by * g.bw + b.bx;
+        b.pw = g.w; b.ph = g.h; b.poff = 0; b.dcidx = b.mb * 6 + b.k;
     } else {
         b.plane = b.k - 3; b.bx = mbx; b.by = mby; b.pw = g.cw; b.ph = g.ch;
         b.poff = g.w * g.h + (b.k - 4) * g.cw * g.ch;
-        b.dcidx = 4 * g.nmb + (b.k - 4) * g.nmb + b.mb;
+        b.dcidx = b.mb * 6 + b.k;
     }
     return b;
 }
@@ -92,11 +94,11 @@ __device__ __forceinline__ MbBlock mb_block(const Geom& g, int mb, int mbx, int 
     if (k < 4) {
         b.poff = 0; b.bx = 2 * mbx + (k & 1); b.by = 2 * mby + (k >> 1); b.pw = g.w; b.ph = g.h; b.pad = 16;
         b.mx = mx; b.my = my;                               // motionCompensation ENC:2185-2186
-        b.dcidx = b.by * g.bw + b.bx;
+        b.dcidx = mb * 6 + k;
     } else {
         b.poff = g.w * g.h + (k - 4) * g.cw * g.ch; b.bx = mbx; b.by = mby; b.pw = g.cw; b.ph = g.ch; b.pad = 8;
         b.mx = mx / 2; b.my = my / 2;                       // CmotionCompensation ENC:2538-2539: truncation toward zero
-        b.dcidx = 4 * g.nmb + (k - 4) * g.nmb + mb;
+        b.dcidx = mb * 6 + k;
     }
     return b;
 }
@@ -196,16 +198,94 @@ __device__ __forceinline__ void mv_predictor(const int16_t* mv, int mbw, int mb,
 
 // `staged` != 0: every block owns one 8-byte shared-memory slot that first holds its input (raw DC as a double when
 // encoding, DC level when decoding) and, once the chain has passed, {reconstructed DC, DC level}; the 115 dependent
-// waves then touch shared memory only and the results are written back at the end (8 bytes per block of shared
-// memory: 19 KB for CIF, so ~11 frames are resident per SM).  Large frames fall back to staged == 0 (int map only,
-// inputs/outputs in global memory inside the chain).
-__global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step st, int decode, int staged)
+// waves then touch shared memory only (8 bytes per block: 19 KB for CIF, so ~11 frames are resident per SM).  All 128
+// threads stage the inputs in and the results out (coalesced over the macroblock-major global arrays, scattered into the
+// plane-raster slots); only the wave walk itself is one warp per plane.  Large frames fall back to staged == 0 (int map
+// only, inputs/outputs in global memory inside the chain).
+// slot index of block k of macroblock mb: luma plane-raster [bh][bw] at 0 (+1 sentinel), Cb [nmb] (+1), Cr [nmb] (+1)
+__device__ __forceinline__ int chain_slot(const Geom& g, int mb, int k)
+{
+    if (k >= 4) return 4 * g.nmb + 1 + (k - 4) * (g.nmb + 1) + mb;
+    const int mby = (int)__umulhi((unsigned)mb, g.magic_mbw), mbx = mb - mby * g.mbw;
+    return (2 * mby + (k >> 1)) * g.bw + 2 * mbx + (k & 1);
+}
+// plane-raster block index i of plane pl (0 Y, 1 Cb, 2 Cr) -> macroblock-major index mb*6 + k
+__device__ __forceinline__ int chain_mbmajor(const Geom& g, int pl, int i)
+{
+    if (pl) return i * 6 + 3 + pl;
+    const int by = (int)__umulhi((unsigned)i, g.magic_bw), bx = i - by * g.bw;
+    return ((by >> 1) * g.mbw + (bx >> 1)) * 6 + (((by & 1) << 1) | (bx & 1));
+}
+__global__ void __launch_bounds__(128) dc_chain_kernel(const __grid_constant__ Geom g, const __grid_constant__ FramePtrs p,
+                                                        const __grid_constant__ Step st, int decode, int staged)
 {
     extern __shared__ __align__(16) unsigned char s_chain[];
     const int nblk = 6 * g.nmb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gop = blockIdx.x;
     const size_t f = (size_t)gop * st.gop_len + st.t;
+    const double* raw = p.dcraw + (size_t)gop * nblk;
+    int32_t* rec = p.dcrec + (size_t)gop * nblk;
+    int16_t* lvf = p.levels + f * g.nmb * 384;
+    const bool chroma = warp > 0;
+    const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh, n = bw * bh;
+    const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
+    const bool walker = warp < 3 && !(warp == 0 && st.intra);   // intra luma DCs are chained inside the wavefront kernel
+    if (staged) {
+        double* slots = (double*)s_chain;
+        int* dc2s = (int*)s_chain;                           // {dc, level} pairs: dc at even ints
+        for (int i6 = threadIdx.x; i6 < nblk; i6 += 128) {
+            const int mb = (int)__umulhi((unsigned)i6, 0x2aaaaaabu), k = i6 - 6 * mb;    // i6 / 6 for i6 < 2^31
+            if (st.intra && k < 4) continue;
+            const int s = chain_slot(g, mb, k);
+            if (decode) dc2s[2 * s + 1] = lvf[i6 * 64];
+            else slots[s] = raw[i6];
+        }
+        if (threadIdx.x < 3) dc2s[2 * (threadIdx.x == 0 ? 4 * g.nmb : 4 * g.nmb + threadIdx.x * (g.nmb + 1))] = 1024;   // sentinels: predictor of block (0,0)
+        __syncthreads();
+        if (walker) {
+            const int base = chroma ? 4 * g.nmb + 1 + (warp - 1) * (g.nmb + 1) : 0;
+            double* slot = slots + base;
+            int* dc2 = dc2s + 2 * base;
+            for (int wv = 0; wv < nwaves; wv++) {
+                const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
+                for (int by = by_lo + lane; by <= by_hi; by += 32) {
+                    const int bx = wv - 2 * by, i = by * bw + bx;
+                    // A.5 without divergent branches: the three neighbours whose median is the predictor (single-neighbour
+                    // cases repeat that neighbour; the first block reads the sentinel); med3 is a true median (ENC:3677-3679)
+                    const bool ur = chroma ? (bx != bw - 1) : ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1));
+                    int a = i - 1, b = i - bw, c = ur ? i - bw + 1 : i - bw - 1;
+                    if (by == 0) { a = bx == 0 ? n : i - 1; b = a; c = a; }
+                    else if (bx == 0) { a = b; c = b; }
+                    const int va = dc2[2 * a], vb = dc2[2 * b], vc = dc2[2 * c];
+                    const int P = max(min(va, vb), min(max(va, vb), vc));
+                    int L;
+                    if (decode) L = dc2[2 * i + 1];
+                    else L = quant_magic(__dsub_rn(slot[i], (double)P), st.magic_dc, chroma);   // DPCM_DC_block: D -= P, then quantise
+                    *(int2*)(dc2 + 2 * i) = make_int2(L * st.qdc + P, L);                      // IQuantization + IDPCM_DC_block
+                }
+                __syncwarp();
+            }
+        } else if (warp == 3 && !st.intra && !decode) {
+            const int16_t* mv = p.mv + f * g.nmb * 2;
+            int16_t* mvd = p.mvd + f * g.nmb * 2;
+            for (int mb = lane; mb < g.nmb; mb += 32) {
+                int px, py;
+                mv_predictor(mv, g.mbw, mb, px, py);
+                mvd[2 * mb] = (int16_t)(mv[2 * mb] - px);
+                mvd[2 * mb + 1] = (int16_t)(mv[2 * mb + 1] - py);
+            }
+        }
+        __syncthreads();
+        for (int i6 = threadIdx.x; i6 < nblk; i6 += 128) {
+            const int mb = (int)__umulhi((unsigned)i6, 0x2aaaaaabu), k = i6 - 6 * mb;
+            if (st.intra && k < 4) continue;
+            const int2 v = *(const int2*)(dc2s + 2 * chain_slot(g, mb, k));
+            rec[i6] = v.x;
+            if (!decode) lvf[i6 * 64] = (int16_t)v.y;
+        }
+        return;
+    }
     if (warp == 3) {
         if (st.intra || decode) return;
         const int16_t* mv = p.mv + f * g.nmb * 2;
@@ -218,69 +298,23 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(Geom g, FramePtrs p, Step
         }
         return;
     }
-    if (warp == 0 && st.intra) return;  // intra luma DCs are chained inside the wavefront kernel
-    const bool chroma = warp > 0;
-    const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh, n = bw * bh;
-    const int base = chroma ? 4 * g.nmb + (warp - 1) * g.nmb : 0;
-    const double* raw = p.dcraw + (size_t)gop * nblk + base;
-    int32_t* rec = p.dcrec + (size_t)gop * nblk + base;
-    int16_t* lvf = p.levels + f * g.nmb * 384;
-    auto level_slot = [&](int i) -> int16_t* {   // plane-raster block index -> DC slot of its levels row
-        const int by = i / bw, bx = i - by * bw;
-        const int mb = chroma ? i : (by >> 1) * g.mbw + (bx >> 1);
-        const int k = chroma ? 3 + warp : ((by & 1) << 1) | (bx & 1);
-        return lvf + (mb * 6 + k) * 64;
-    };
-    const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
-    if (staged) {
-        // slots: luma n+1, Cb nmb+1, Cr nmb+1 (the +1 is a sentinel holding 1024, the predictor of the first block)
-        double* slot = (double*)s_chain + base + warp;   // 8 bytes per block
-        int* dc2 = (int*)slot;                           // {dc, level} pairs: dc at even ints
-        if (decode) for (int i = lane; i < n; i += 32) dc2[2 * i + 1] = *level_slot(i);
-        else for (int i = lane; i < n; i += 32) slot[i] = raw[i];
-        if (lane == 0) dc2[2 * n] = 1024;
-        __syncwarp();
-        for (int wv = 0; wv < nwaves; wv++) {
-            const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
-            for (int by = by_lo + lane; by <= by_hi; by += 32) {
-                const int bx = wv - 2 * by, i = by * bw + bx;
-                // A.5 without divergent branches: the three neighbours whose median is the predictor (single-neighbour
-                // cases repeat that neighbour; the first block reads the sentinel); med3 is a true median (ENC:3677-3679)
-                const bool ur = chroma ? (bx != bw - 1) : ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1));
-                int a = i - 1, b = i - bw, c = ur ? i - bw + 1 : i - bw - 1;
-                if (by == 0) { a = bx == 0 ? n : i - 1; b = a; c = a; }
-                else if (bx == 0) { a = b; c = b; }
-                const int va = dc2[2 * a], vb = dc2[2 * b], vc = dc2[2 * c];
-                const int P = max(min(va, vb), min(max(va, vb), vc));
-                int L;
-                if (decode) L = dc2[2 * i + 1];
-                else L = quant_magic(__dsub_rn(slot[i], (double)P), st.magic_dc, chroma);   // DPCM_DC_block: D -= P, then quantise
-                *(int2*)(dc2 + 2 * i) = make_int2(L * st.qdc + P, L);                      // IQuantization + IDPCM_DC_block
-            }
-            __syncwarp();
-        }
-        for (int i = lane; i < n; i += 32) {
-            const int2 v = *(const int2*)(dc2 + 2 * i);
-            rec[i] = v.x;
-            if (!decode) *level_slot(i) = (int16_t)v.y;
-        }
-        return;
-    }
-    int* dc = (int*)s_chain + base;                      // Y[bh*bw], Cb[nmb], Cr[nmb]
+    if (!walker) return;
+    int* dc = (int*)s_chain + (chroma ? 4 * g.nmb + (warp - 1) * g.nmb : 0);   // Y[bh*bw], Cb[nmb], Cr[nmb]
     for (int wv = 0; wv < nwaves; wv++) {
         const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
         for (int by = by_lo + lane; by <= by_hi; by += 32) {
             const int bx = wv - 2 * by, i = by * bw + bx;
+            const int i6 = chain_mbmajor(g, warp, i);
             const int P = chroma ? dc_pred_chroma(dc, bw, bx, by) : dc_pred_luma(dc, bw, bx, by);
             int L;
-            if (decode) L = (int)*level_slot(i);
+            if (decode) L = (int)lvf[i6 * 64];
             else {
-                L = quant_magic(__dsub_rn(raw[i], (double)P), st.magic_dc, chroma);
-                *level_slot(i) = (int16_t)L;
+                L = quant_magic(__dsub_rn(raw[i6], (double)P), st.magic_dc, chroma);
+                lvf[i6 * 64] = (int16_t)L;
             }
             const int v = L * st.qdc + P;
             dc[i] = v;
-            rec[i] = v;
+            rec[i6] = v;
         }
         __syncwarp();
     }

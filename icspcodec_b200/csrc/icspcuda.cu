@@ -2,6 +2,7 @@
 // Host side only orchestrates: one context = one GPU, one stream, SoA device buffers sized for max_frames.
 #include "../../include/icspcuda.h"
 #include "icsp_kernels.cuh"
+#include "icsp_transform.cuh"
 #include "icsp_entropy.cuh"
 
 #include <algorithm>
@@ -63,6 +64,8 @@ struct icsp_ctx {
     unsigned long long* d_mezero = nullptr;
     void* d_shim = nullptr;
     size_t shim_bytes = 0;
+    double* d_dct_tap = nullptr;              // debug tap of the forward DCT (only while icsp_encode_gops_tap runs)
+    bool tr_v1 = false;                       // ICSP_TR_V1=1: first-generation transform kernels (A/B comparisons)
     // entropy coder (allocated on first use)
     uint32_t* d_blkbits = nullptr;
     unsigned long long *d_framebits = nullptr, *d_streambits = nullptr, *d_streamoff = nullptr, *d_chunktotal = nullptr;
@@ -114,6 +117,10 @@ int geom_init(Geom& g, int w, int h)
     g.cw = w / 2; g.ch = h / 2; g.bw = w / 8; g.bh = h / 8; g.fb = w * h * 3 / 2;
     g.magic_bw = (unsigned)((0x100000000ull + g.bw - 1) / g.bw);
     g.magic_mbw = (unsigned)((0x100000000ull + g.mbw - 1) / g.mbw);
+    g.magic_mbw2 = g.mbw > 2 ? (unsigned)((0x100000000ull + g.mbw - 3) / (g.mbw - 2)) : 0u;
+    for (int k = 0; k < 4; k++) { g.d_pix[k] = (k >> 1) * 8 * g.w + (k & 1) * 8; g.d_dc[k] = (k >> 1) * g.bw + (k & 1); }
+    g.d_pix[4] = 0; g.d_pix[5] = g.cw * g.ch;
+    g.d_dc[4] = 4 * g.nmb; g.d_dc[5] = 5 * g.nmb;
     return 0;
 }
 
@@ -149,6 +156,10 @@ int upload_tables(icsp_ctx* c)
             for (int k = 1; k < 8; k++) mag[t][k] = t == 0 ? (double)(float)LIT[k] : LIT[k];
         }
         CU(cudaMemcpyToSymbol(g_mag, mag, sizeof(mag)));
+        double mag2[2][16];
+        for (int t = 0; t < 2; t++)
+            for (int k = 0; k < 8; k++) { mag2[t][k] = mag[t][k]; mag2[t][8 + k] = 0.25 * mag[t][k]; }   // exact scaling
+        CU(cudaMemcpyToSymbol(g_mag2, mag2, sizeof(mag2)));
     }
     {
         uint2 izcol[8], izrow[8];
@@ -229,6 +240,17 @@ struct LaunchScope {
     }
 };
 
+Step make_step(int gop_len, int t, int qdc, int qac)
+{
+    Step st{};
+    st.gop_len = gop_len; st.t = t; st.qdc = qdc; st.qac = qac; st.intra = t == 0 ? 1 : 0;
+    st.magic_ac = (unsigned)((0x80000000ull + qac - 1) / qac);
+    st.magic_dc = (unsigned)((0x80000000ull + qdc - 1) / qdc);
+    st.qmode_ac = qac <= 128 ? 0 : 1;                 // div_m19 is exact while 4080*qac < 2^19
+    st.m19_ac = (1 << 19) / qac + 1;
+    return st;
+}
+
 // pointers of the chunk that starts at GOP g0 (frame g0*gop_len): kernels index GOPs from 0 inside a chunk
 FramePtrs frame_ptrs(icsp_ctx* c, int g0 = 0, int gop_len = 1)
 {
@@ -240,6 +262,7 @@ FramePtrs frame_ptrs(icsp_ctx* c, int g0 = 0, int gop_len = 1)
     p.dcraw = c->d_dcraw + G0 * nmb * 6; p.dcrec = c->d_dcrec + G0 * nmb * 6;
     p.mestate = c->d_mestate + G0 * nmb; p.memoves = c->d_memoves + G0 * nmb; p.meflag = c->d_meflag + G0;
     p.mezero = c->d_mezero + G0 * nmb * 8;
+    p.dct_tap = c->d_dct_tap ? c->d_dct_tap + f0 * nmb * 384 : nullptr;
     return p;
 }
 
@@ -287,6 +310,18 @@ void hi_end(icsp_ctx* c, cudaStream_t s, int idx)
     cudaStreamWaitEvent(s, c->ev_hi[idx][1], 0);
 }
 
+template <bool INTRA, bool QFAST>
+void launch_fdct2_t(const Geom& g, const FramePtrs& p, const Step& st, dim3 grid, cudaStream_t s)
+{
+    if (p.dct_tap) fdct_quant_kernel2<INTRA, QFAST, true><<<grid, TR2_THREADS, 0, s>>>(g, p, st);
+    else fdct_quant_kernel2<INTRA, QFAST, false><<<grid, TR2_THREADS, 0, s>>>(g, p, st);
+}
+void launch_fdct2(const Geom& g, const FramePtrs& p, const Step& st, dim3 grid, cudaStream_t s)
+{
+    if (st.intra) { if (st.qmode_ac == 0) launch_fdct2_t<true, true>(g, p, st, grid, s); else launch_fdct2_t<true, false>(g, p, st, grid, s); }
+    else { if (st.qmode_ac == 0) launch_fdct2_t<false, true>(g, p, st, grid, s); else launch_fdct2_t<false, false>(g, p, st, grid, s); }
+}
+
 // motion estimation of step t for every GOP: speculative state-0 search, then the exact carried-state fallback
 // (no-ops unless some search of the frame broke early)
 int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream_t s)
@@ -316,7 +351,7 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     const Geom& g = c->g;
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
     for (int t = 0; t < gop_len; t++) {
-        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
+        const Step st = make_step(gop_len, t, qdc, qac);
         const int per = TR_THREADS / 8;
         dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
         if (st.intra) {
@@ -329,14 +364,23 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             const int rc = launch_me(c, p, st, G, s);
             if (rc) return rc;
         }
-        { LaunchScope ls(c, st.intra ? K_FDCT_C : K_FDCT, s); fdct_quant_kernel<<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        {
+            LaunchScope ls(c, st.intra ? K_FDCT_C : K_FDCT, s);
+            if (c->tr_v1) fdct_quant_kernel<<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
+            else launch_fdct2(g, p, st, lgrid, s);
+        }
         {
             int hi;
             cudaStream_t h = hi_begin(c, s, hi);
             { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 0, c->chain_staged); }
             hi_end(c, s, hi);
         }
-        { LaunchScope ls(c, st.intra ? K_IDCT_ENC_C : K_IDCT_ENC, s); idct_recon_kernel<0><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        {
+            LaunchScope ls(c, st.intra ? K_IDCT_ENC_C : K_IDCT_ENC, s);
+            if (c->tr_v1) idct_recon_kernel<0><<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
+            else if (st.intra) idct_recon_kernel2<0, true><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
+            else idct_recon_kernel2<0, false><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
+        }
     }
     return ICSP_OK;
 }
@@ -346,7 +390,7 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     const Geom& g = c->g;
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
     for (int t = 0; t < gop_len; t++) {
-        Step st{gop_len, t, qdc, qac, t == 0 ? 1 : 0, (unsigned)((0x80000000ull + qac - 1) / qac), (unsigned)((0x80000000ull + qdc - 1) / qdc)};
+        const Step st = make_step(gop_len, t, qdc, qac);
         const int per = TR_THREADS / 8;
         dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
         if (st.intra) {
@@ -365,7 +409,12 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
             { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 1, c->chain_staged); }
             hi_end(c, s, hi);
         }
-        { LaunchScope ls(c, st.intra ? K_IDCT_DEC_C : K_IDCT_DEC, s); idct_recon_kernel<1><<<lgrid, TR_THREADS, 0, s>>>(g, p, st); }
+        {
+            LaunchScope ls(c, st.intra ? K_IDCT_DEC_C : K_IDCT_DEC, s);
+            if (c->tr_v1) idct_recon_kernel<1><<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
+            else if (st.intra) idct_recon_kernel2<1, true><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
+            else idct_recon_kernel2<1, false><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
+        }
     }
     return ICSP_OK;
 }
@@ -526,6 +575,7 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     c->me_smem = me_smem_bytes(c->me);
     c->me_frame_smem = me_frame_smem_bytes(c->me);
     if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
+    if (const char* e = getenv("ICSP_TR_V1")) c->tr_v1 = atoi(e) != 0;
     c->intra_smem = intra_smem_bytes(g);
     c->chain_smem = (size_t)(6 * g.nmb + 3) * 8 + 32;  // staged: one 8-byte slot per block + a sentinel per plane
     if (c->chain_smem > 100 * 1024) { c->chain_staged = 0; c->chain_smem = (size_t)6 * g.nmb * sizeof(int) + 32; }
@@ -997,7 +1047,7 @@ int icsp_me_sad(icsp_ctx* c, const uint8_t* cur_y, const uint8_t* ref_y, int n, 
     // pair i: reference luma -> rec frame 2i, current luma -> cur frame 2i+1 (gop_len 2, step 1)
     CU(cudaMemcpy2DAsync(c->d_rec, (size_t)2 * g.fb, ref_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpy2DAsync(c->d_cur + g.fb, (size_t)2 * g.fb, cur_y, ysz, ysz, n, cudaMemcpyHostToDevice, c->stream));
-    Step st{2, 1, 1, 1, 0, 0u, 0u};
+    const Step st = make_step(2, 1, 1, 1);
     int rc = launch_me(c, frame_ptrs(c), st, n, c->stream);
     if (rc) return rc;
     CU(cudaMemcpy2DAsync(mv, (size_t)g.nmb * 4, c->d_mv + (size_t)g.nmb * 2, (size_t)g.nmb * 8, (size_t)g.nmb * 4, n,
