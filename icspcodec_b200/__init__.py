@@ -3,4 +3,4 @@
 Product = icspcodec_b200/libicspcuda.so (C ABI, include/icspcuda.h) + the C++ host tools in
 icspcodec_b200/host (icspenc, icspdec).  The Python modules are bindings for tests and bench.py.
 """
-from .api import EncResult, IcspCuda, IcspError, PinnedArray  # noqa: F401
+from .api import EncResult, IcspCuda, IcspError, PinnedArray, finish_stream, stream_header  # noqa: F401

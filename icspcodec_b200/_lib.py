@@ -12,7 +12,7 @@ MAX_KERNELS = 32
 
 
 class EncOut(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("levels", "acflag", "mpm", "ipm", "mvd", "mv", "minsad", "recon")]
+    _fields_ = [(n, C.c_void_p) for n in ("levels", "acflag", "mpm", "ipm", "mvd", "mv", "minsad", "recon", "dct")]
 
 
 class DecIn(C.Structure):
@@ -42,6 +42,7 @@ EXPORTS = [
     "icsp_event_record", "icsp_event_elapsed_ms",
     "icsp_host_alloc", "icsp_host_alloc_upload", "icsp_host_free",
     "icsp_configure", "icsp_encode_streams", "icsp_entropy_run", "icsp_bits_download", "icsp_finish_body", "icsp_bits_bound", "icsp_enc_sse", "icsp_bits_row_index", "icsp_decode_streams",
+    "icsp_quant", "icsp_intra_frame", "icsp_inter_frame",
 ]
 
 _lib = None
@@ -77,6 +78,9 @@ def load() -> C.CDLL:
     lib.icsp_me_sad.argtypes = [vp, vp, vp, i, vp, vp]
     lib.icsp_dct8x8.argtypes = [vp, vp, i, vp]
     lib.icsp_idct8x8.argtypes = [vp, vp, i, i, vp]
+    lib.icsp_quant.argtypes = [vp, vp, i, i, i, i, vp, vp]
+    lib.icsp_intra_frame.argtypes = [vp, vp, i, i, i, C.POINTER(EncOut)]
+    lib.icsp_inter_frame.argtypes = [vp, vp, vp, i, i, i, C.POINTER(EncOut)]
     lib.icsp_set_profiling.argtypes = [vp, i]
     lib.icsp_reset_stats.argtypes = [vp]
     lib.icsp_get_stats.argtypes = [vp, C.POINTER(KernelStat), i]

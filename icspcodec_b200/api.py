@@ -27,6 +27,7 @@ class EncResult:
     mv: np.ndarray       # int16 [n][nmb][2]
     minsad: np.ndarray   # int32 [n][nmb]
     recon: np.ndarray    # uint8 [n][fb]
+    dct: np.ndarray | None = None   # f64 [n][nmb][6][64] debug tap (only when asked for)
 
 
 def _ptr(a: np.ndarray | None):
@@ -62,6 +63,17 @@ def stream_header(w: int, h: int, qp_dc: int, qp_ac: int, intra_period: int) -> 
     return bytes([0, 73, 67, 83, 80, h & 255, h >> 8, w & 255, w >> 8, qp_dc & 255, qp_ac & 255, 0, outro & 255, outro >> 8])
 
 
+def finish_stream(body: np.ndarray, nbits: int, w: int, h: int, qp_dc: int, qp_ac: int, intra_period: int) -> bytes:
+    """MSB-first body bytes (ceil(nbits/8), as icsp_encode_streams returns them) -> the reference-format file: 14-byte header
+    + nbits/8+1 body bytes with the tail bits right-aligned in the last byte (makebitstream ENC:4873-4895)."""
+    b = bytearray(bytes(body[: (nbits + 7) // 8]))
+    if nbits % 8:
+        b[-1] = b[-1] >> (8 - nbits % 8)
+    else:
+        b += b"\x00"
+    return stream_header(w, h, qp_dc, qp_ac, intra_period) + bytes(b)
+
+
 class IcspCuda:
     """One context = one GPU + one stream + device SoA buffers for up to `max_frames` frames."""
 
@@ -94,7 +106,11 @@ class IcspCuda:
             raise IcspError(f"{what} failed ({rc}): {self.lib.icsp_last_error(self.h_ctx).decode()}")
 
     # ---- encoder -----------------------------------------------------------------------------------
-    def alloc_result(self, n: int, pinned: bool = False) -> EncResult:
+    def alloc_result(self, n: int, pinned: bool = False, with_dct: bool = False) -> EncResult:
+        if with_dct:
+            r = self.alloc_result(n, pinned)
+            r.dct = np.zeros((n, self.nmb, 6, 64), np.float64)
+            return r
         shapes = dict(levels=((n, self.nmb, 6, 64), np.int16), acflag=((n, self.nmb, 6), np.uint8),
                       mpm=((n, self.nmb, 4), np.uint8), ipm=((n, self.nmb, 4), np.uint8),
                       mvd=((n, self.nmb, 2), np.int16), mv=((n, self.nmb, 2), np.int16),
@@ -115,18 +131,44 @@ class IcspCuda:
         for name in ("levels", "acflag", "mpm", "ipm", "mvd", "mv", "minsad", "recon"):
             want = fields is None or name in fields
             setattr(o, name, _ptr(getattr(res, name)) if want else None)
+        o.dct = _ptr(res.dct) if res.dct is not None and (fields is None or "dct" in fields) else None
         return o
 
     def encode_gops(self, frames: np.ndarray, n_gops: int, gop_len: int, qp_dc: int, qp_ac: int,
-                    out: EncResult | None = None, fields=None) -> EncResult:
+                    out: EncResult | None = None, fields=None, with_dct: bool = False) -> EncResult:
         frames = np.ascontiguousarray(frames, np.uint8)
         n = n_gops * gop_len
         if frames.size != n * self.fb:
             raise IcspError(f"expected {n} frames of {self.fb} bytes")
-        res = out or self.alloc_result(n)
+        res = out or self.alloc_result(n, with_dct=with_dct)
         o = self._enc_out(res, fields)
         self._chk(self.lib.icsp_encode_gops(self.h_ctx, _ptr(frames), n_gops, gop_len, qp_dc, qp_ac, C.byref(o)), "icsp_encode_gops")
         return res
+
+    def intra_frame(self, frames: np.ndarray, qp_dc: int, qp_ac: int, with_dct: bool = False) -> EncResult:
+        """intraPrediction (ENC:556-643) on independent frames."""
+        frames = np.ascontiguousarray(frames, np.uint8).reshape(-1, self.fb)
+        res = self.alloc_result(frames.shape[0], with_dct=with_dct)
+        o = self._enc_out(res)
+        self._chk(self.lib.icsp_intra_frame(self.h_ctx, _ptr(frames), frames.shape[0], qp_dc, qp_ac, C.byref(o)), "icsp_intra_frame")
+        return res
+
+    def inter_frame(self, cur: np.ndarray, prev_recon: np.ndarray, qp_dc: int, qp_ac: int, with_dct: bool = False) -> EncResult:
+        """interPrediction(cur, prev) (ENC:1986-2072) on independent pairs: cur[i] coded against the reconstruction prev_recon[i]."""
+        cur = np.ascontiguousarray(cur, np.uint8).reshape(-1, self.fb)
+        prev_recon = np.ascontiguousarray(prev_recon, np.uint8).reshape(-1, self.fb)
+        res = self.alloc_result(cur.shape[0], with_dct=with_dct)
+        o = self._enc_out(res)
+        self._chk(self.lib.icsp_inter_frame(self.h_ctx, _ptr(cur), _ptr(prev_recon), cur.shape[0], qp_dc, qp_ac, C.byref(o)), "icsp_inter_frame")
+        return res
+
+    def quant(self, dct: np.ndarray, qp_dc: int, qp_ac: int, chroma: bool = False):
+        """Quantization_block / CQuantization_block (ENC:2750-2824, 4610-4656): (levels int32 [n][64] raster order, acflag uint8 [n])."""
+        dct = np.ascontiguousarray(dct, np.float64).reshape(-1, 64)
+        lv = np.zeros(dct.shape, np.int32)
+        ac = np.zeros(dct.shape[0], np.uint8)
+        self._chk(self.lib.icsp_quant(self.h_ctx, _ptr(dct), dct.shape[0], qp_dc, qp_ac, int(chroma), _ptr(lv), _ptr(ac)), "icsp_quant")
+        return lv, ac
 
     def encode_sequence(self, frames: np.ndarray, qp_dc: int, qp_ac: int, intra_period: int) -> EncResult:
         """Frame loop of single_thread_encoding (ENC:217-245): I-frame iff n % intra_period == 0 (0 = all intra).
@@ -143,7 +185,7 @@ class IcspCuda:
             parts.append((full * ip, 1, n - full * ip))
         for start, ng, gl in parts:
             cnt = ng * gl
-            sub = EncResult(**{k: getattr(res, k)[start:start + cnt] for k in res.__dataclass_fields__})
+            sub = EncResult(**{k: (None if getattr(res, k) is None else getattr(res, k)[start:start + cnt]) for k in res.__dataclass_fields__})
             self.encode_gops(frames[start:start + cnt], ng, gl, qp_dc, qp_ac, out=sub)
         return res
 
@@ -245,12 +287,20 @@ class IcspCuda:
         body = np.frombuffer(data, np.uint8)[14:]
         rows = np.ascontiguousarray(rows, np.uint64).reshape(nframes, self.h // 16)
         full, tail = divmod(nframes, ip)
-        so, sb = np.zeros(1, np.uint64), np.array([body.size], np.uint64)
         outs = []
+
+        def part(f0: int, f1: int, ngops: int, glen: int):
+            # only the bytes these frames need go up (icspdec does the same): [start, end) of the body, start 4-byte aligned,
+            # row offsets rebased to it
+            start = (int(rows[f0][0]) // 8) & ~3
+            end = body.size if f1 >= nframes else int(rows[f1][0]) // 8 + 1
+            sub = np.ascontiguousarray(body[start:end])
+            so, sb = np.zeros(1, np.uint64), np.array([sub.size], np.uint64)
+            return self.decode_streams(sub, so, sb, rows[f0:f1] - np.uint64(start * 8), 1, ngops, glen, qdc, qac)
         if full:
-            outs.append(self.decode_streams(body, so, sb, rows[: full * ip], 1, full, ip, qdc, qac))
+            outs.append(part(0, full * ip, full, ip))
         if tail:
-            outs.append(self.decode_streams(body, so, sb, rows[full * ip:], 1, 1, tail, qdc, qac))
+            outs.append(part(full * ip, nframes, 1, tail))
         return np.concatenate(outs)
 
     # ---- decoder -----------------------------------------------------------------------------------
@@ -286,7 +336,7 @@ class IcspCuda:
         ro = np.ascontiguousarray(row_bit_offset, np.uint64)
         if so.size != n_streams or sb.size != n_streams or ro.size != n * (self.h // 16):
             raise IcspError("decode_streams: table sizes do not match the stream geometry")
-        if int(so[-1] + sb[-1]) > bits.size:
+        if any(int(o) > bits.size or int(b) > bits.size - int(o) for o, b in zip(so, sb)):      # Python ints: no uint64 wrap-around
             raise IcspError("decode_streams: stream table points past the bits buffer")
         if out is None:
             out = np.zeros((n, self.fb), np.uint8)

@@ -544,6 +544,11 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
                 fdct_row(e, t, M0);
                 group_transpose(t, s_tile[grp], r);
                 fdct_col(t, r, D, M0);
+                if (p.dct_tap && active) {     // debug tap: forward DCT output before the DC predictor is subtracted
+                    double* tap = p.dct_tap + ((f * g.nmb + mb) * 6 + k) * 64 + r;
+#pragma unroll
+                    for (int v = 0; v < 8; v++) tap[v * 8] = D[v];
+                }
                 if (r == 0) D[0] = __dsub_rn(D[0], (double)P);
                 int nz = 0, L[8];
 #pragma unroll
@@ -1015,6 +1020,23 @@ __global__ void idct8x8_kernel(const int32_t* in, double* out, int n)
     if (blk < n)
 #pragma unroll
         for (int y = 0; y < 8; y++) out[(size_t)blk * 64 + y * 8 + r] = R[y];
+}
+
+// Quantization_block (ENC:2750-2796) / CQuantization_block (ENC:4610-4656) on n stand-alone blocks: raster order in and out,
+// QstepDC at [0][0], QstepAC elsewhere, luma truncates and chroma floors before the integer division; ACflag = all 63 AC == 0
+__global__ void __launch_bounds__(256) quant8x8_kernel(const double* in, int32_t* out, uint8_t* acflag, int n, unsigned magic_dc, unsigned magic_ac, int chroma)
+{
+    __shared__ int s_nz[4];
+    const int b = threadIdx.x >> 6, i = threadIdx.x & 63, blk = blockIdx.x * 4 + b;
+    if (i == 0) s_nz[b] = 0;
+    __syncthreads();
+    if (blk < n) {
+        const int L = quant_magic(in[(size_t)blk * 64 + i], i == 0 ? magic_dc : magic_ac, chroma != 0);
+        out[(size_t)blk * 64 + i] = L;
+        if (i != 0 && L != 0) atomicOr(&s_nz[b], 1);
+    }
+    __syncthreads();
+    if (blk < n && i == 0 && acflag) acflag[blk] = s_nz[b] ? 0 : 1;
 }
 
 // decoder: motion vector reconstruction mv = mvd + Pm over already reconstructed neighbours (DEC:4301-4370).

@@ -24,14 +24,15 @@ thread_local char g_create_error[256] = "";
 enum KernelId {
     K_INTRA_ENC = 0, K_INTRA_DEC, K_FDCT, K_DCCHAIN, K_IDCT_ENC, K_IDCT_DEC, K_ME_SAD, K_ME_ZERO, K_ME_CHAIN, K_ME_FIXUP,
     K_MV_RECON, K_DCT_SHIM, K_IDCT_SHIM, K_EN_SIZE, K_EN_FSCAN, K_EN_SSCAN, K_EN_ZERO, K_EN_PACK, K_FDCT_C, K_IDCT_ENC_C,
-    K_IDCT_DEC_C, K_SSE, K_ROWIDX, K_PARSE, K_COUNT
+    K_IDCT_DEC_C, K_SSE, K_ROWIDX, K_PARSE, K_QUANT_SHIM, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "intra_luma_kernel<enc>", "intra_luma_kernel<dec>", "fdct_quant_kernel", "dc_chain_kernel", "idct_recon_kernel<enc>",
     "idct_recon_kernel<dec>", "me_sad_kernel", "me_zero_kernel", "me_chain_kernel", "me_sad_kernel(fixup)",
     "mv_recon_kernel", "dct8x8_kernel", "idct8x8_kernel", "entropy_size_kernel", "entropy_frame_scan_kernel",
     "entropy_stream_scan_kernels", "entropy_zero_kernel", "entropy_pack_kernel", "fdct_quant_kernel(intra: chroma only)",
-    "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)", "plane_sse_kernel", "row_index_kernel", "parse_rows_kernel"};
+    "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)", "plane_sse_kernel", "row_index_kernel", "parse_rows_kernel",
+    "quant8x8_kernel"};
 
 struct Pending { int k; cudaEvent_t a, b; };
 
@@ -346,41 +347,50 @@ int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream
 }
 
 // every step of GOPs [g0, g0+G) on stream s
-int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+// one step (intra-GOP frame index st.t) of GOPs [g0, g0+G) on stream s
+int encode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, cudaStream_t s)
 {
     const Geom& g = c->g;
+    const int per = TR_THREADS / 8;
+    dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
+    const bool v1 = c->tr_v1 && !p.dct_tap;   // the DCT tap exists in the second-generation kernels only
+    if (st.intra) {
+        int hi;
+        cudaStream_t h = hi_begin(c, s, hi);
+        { LaunchScope ls(c, K_INTRA_ENC, h);
+          intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr); }
+        hi_end(c, s, hi);
+    } else {
+        const int rc = launch_me(c, p, st, G, s);
+        if (rc) return rc;
+    }
+    {
+        LaunchScope ls(c, st.intra ? K_FDCT_C : K_FDCT, s);
+        if (v1) fdct_quant_kernel<<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
+        else launch_fdct2(g, p, st, lgrid, s);
+    }
+    {
+        int hi;
+        cudaStream_t h = hi_begin(c, s, hi);
+        { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 0, c->chain_staged); }
+        hi_end(c, s, hi);
+    }
+    {
+        LaunchScope ls(c, st.intra ? K_IDCT_ENC_C : K_IDCT_ENC, s);
+        if (v1) idct_recon_kernel<0><<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
+        else if (st.intra) idct_recon_kernel2<0, true><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
+        else idct_recon_kernel2<0, false><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
+    }
+    return ICSP_OK;
+}
+
+// every step of GOPs [g0, g0+G) on stream s
+int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+{
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
     for (int t = 0; t < gop_len; t++) {
-        const Step st = make_step(gop_len, t, qdc, qac);
-        const int per = TR_THREADS / 8;
-        dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
-        if (st.intra) {
-            int hi;
-            cudaStream_t h = hi_begin(c, s, hi);
-            { LaunchScope ls(c, K_INTRA_ENC, h);
-              intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr); }
-            hi_end(c, s, hi);
-        } else {
-            const int rc = launch_me(c, p, st, G, s);
-            if (rc) return rc;
-        }
-        {
-            LaunchScope ls(c, st.intra ? K_FDCT_C : K_FDCT, s);
-            if (c->tr_v1) fdct_quant_kernel<<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
-            else launch_fdct2(g, p, st, lgrid, s);
-        }
-        {
-            int hi;
-            cudaStream_t h = hi_begin(c, s, hi);
-            { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 0, c->chain_staged); }
-            hi_end(c, s, hi);
-        }
-        {
-            LaunchScope ls(c, st.intra ? K_IDCT_ENC_C : K_IDCT_ENC, s);
-            if (c->tr_v1) idct_recon_kernel<0><<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
-            else if (st.intra) idct_recon_kernel2<0, true><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
-            else idct_recon_kernel2<0, false><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
-        }
+        const int rc = encode_step(c, p, make_step(gop_len, t, qdc, qac), g0, G, s);
+        if (rc) return rc;
     }
     return ICSP_OK;
 }
@@ -574,6 +584,7 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     c->me = me_layout(g);
     c->me_smem = me_smem_bytes(c->me);
     c->me_frame_smem = me_frame_smem_bytes(c->me);
+    if (const char* e = getenv("ICSP_ME_SMEM_MIN")) c->me_frame_smem = std::max(c->me_frame_smem, (size_t)atoi(e));   // experiments: cap ME CTAs per SM
     if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
     if (const char* e = getenv("ICSP_TR_V1")) c->tr_v1 = atoi(e) != 0;
     c->intra_smem = intra_smem_bytes(g);
@@ -703,7 +714,7 @@ int icsp_enc_download(icsp_ctx* c, int n, const icsp_enc_out* o)
     return ICSP_OK;
 }
 
-int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len, int qdc, int qac, const icsp_enc_out* out)
+static int icsp_encode_gops_impl(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len, int qdc, int qac, const icsp_enc_out* out)
 {
     int rc = check_run(c, n_gops, gop_len, qdc, qac);
     if (rc) return rc;
@@ -712,6 +723,13 @@ int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len
     const Geom& g = c->g;
     const size_t nmb = (size_t)g.nmb;
     const int n = n_gops * gop_len;
+    if (out->dct) {   // debug tap of the forward DCT: device buffer for this call only
+        if (cudaMalloc(&c->d_dct_tap, (size_t)n * nmb * 384 * sizeof(double)) != cudaSuccess) {
+            c->d_dct_tap = nullptr;
+            return fail(c, ICSP_ERR_NOMEM, "icsp_enc_out.dct: %zu bytes of device memory for the DCT tap", (size_t)n * nmb * 384 * sizeof(double));
+        }
+    }
+    struct TapGuard { icsp_ctx* c; ~TapGuard() { if (c->d_dct_tap) { cudaDeviceSynchronize(); cudaFree(c->d_dct_tap); c->d_dct_tap = nullptr; } } } tap_guard{c};
     // inter frames leave mpm/ipm untouched and intra frames leave mvd/mv/minsad untouched: clear them so the SoA
     // rows of the other frame type read as zero, as documented
     CU(cudaMemsetAsync(c->d_mpm, 0, (size_t)n * nmb * 4, c->stream));
@@ -745,12 +763,57 @@ int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len
         if (out->mv) CU(cudaMemcpyAsync(out->mv + f0 * nmb * 2, c->d_mv + f0 * nmb * 2, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
         if (out->minsad) CU(cudaMemcpyAsync(out->minsad + f0 * nmb, c->d_minsad + f0 * nmb, cnt * nmb * 4, cudaMemcpyDeviceToHost, d));
         if (out->recon) CU(cudaMemcpyAsync(out->recon + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, d));
+        if (out->dct) CU(cudaMemcpyAsync(out->dct + f0 * nmb * 384, c->d_dct_tap + f0 * nmb * 384, cnt * nmb * 384 * sizeof(double), cudaMemcpyDeviceToHost, d));
     }
     if ((rc = join_streams(c))) return rc;
     CU(cudaEventRecord(c->ev_join[0], c->s_down));
     CU(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
     CU(cudaEventRecord(c->ev_join[1], c->s_up));
     CU(cudaStreamWaitEvent(c->stream, c->ev_join[1], 0));
+    CU(cudaGetLastError());
+    return icsp_sync(c);
+}
+
+// intraPrediction (ENC:556-643) on n independent frames
+int icsp_intra_frame(icsp_ctx* c, const uint8_t* frames, int n, int qdc, int qac, const icsp_enc_out* out)
+{
+    return icsp_encode_gops(c, frames, n, 1, qdc, qac, out);
+}
+
+// interPrediction(cur, prev) (ENC:1986-2072) on n independent pairs: pair i = device frames 2i (reference: only its
+// reconstruction is needed) and 2i+1 (current), step t = 1 of a GOP of length 2
+static int icsp_inter_frame_impl(icsp_ctx* c, const uint8_t* cur, const uint8_t* prev_recon, int n, int qdc, int qac, const icsp_enc_out* out)
+{
+    int rc = check_run(c, n, 2, qdc, qac);
+    if (rc) return rc;
+    if (!cur || !prev_recon || !out) return fail(c, ICSP_ERR_PARAM, "icsp_inter_frame: NULL frames/out");
+    CU(cudaSetDevice(c->device));
+    const Geom& g = c->g;
+    const size_t nmb = (size_t)g.nmb, fb = (size_t)g.fb;
+    if (out->dct) {
+        if (cudaMalloc(&c->d_dct_tap, (size_t)2 * n * nmb * 384 * sizeof(double)) != cudaSuccess) {
+            c->d_dct_tap = nullptr;
+            return fail(c, ICSP_ERR_NOMEM, "icsp_enc_out.dct: device memory for the DCT tap");
+        }
+    }
+    struct TapGuard { icsp_ctx* c; ~TapGuard() { if (c->d_dct_tap) { cudaDeviceSynchronize(); cudaFree(c->d_dct_tap); c->d_dct_tap = nullptr; } } } tap_guard{c};
+    cudaStream_t s = c->stream;
+    CU(cudaMemcpy2DAsync(c->d_rec, 2 * fb, prev_recon, fb, fb, n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(c->d_cur + fb, 2 * fb, cur, fb, fb, n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(c->d_mpm, 0, (size_t)2 * n * nmb * 4, s));
+    CU(cudaMemsetAsync(c->d_ipm, 0, (size_t)2 * n * nmb * 4, s));
+    if ((rc = encode_step(c, frame_ptrs(c, 0, 2), make_step(2, 1, qdc, qac), 0, n, s))) return rc;
+    // frame 2i+1 of every array -> row i of the caller's
+    auto down = [&](void* dst, const void* src, size_t per_frame) -> int {
+        if (!dst) return ICSP_OK;
+        CU(cudaMemcpy2DAsync(dst, per_frame, (const char*)src + per_frame, 2 * per_frame, per_frame, n, cudaMemcpyDeviceToHost, s));
+        return ICSP_OK;
+    };
+    if ((rc = down(out->levels, c->d_levels, nmb * 384 * 2)) || (rc = down(out->acflag, c->d_acflag, nmb * 6)) ||
+        (rc = down(out->mpm, c->d_mpm, nmb * 4)) || (rc = down(out->ipm, c->d_ipm, nmb * 4)) || (rc = down(out->mvd, c->d_mvd, nmb * 4)) ||
+        (rc = down(out->mv, c->d_mv, nmb * 4)) || (rc = down(out->minsad, c->d_minsad, nmb * 4)) || (rc = down(out->recon, c->d_rec, fb)) ||
+        (rc = down(out->dct, c->d_dct_tap, nmb * 384 * sizeof(double))))
+        return rc;
     CU(cudaGetLastError());
     return icsp_sync(c);
 }
@@ -776,14 +839,20 @@ static int check_streams(icsp_ctx* c, int n_streams, int gops_per_stream, int go
     if (n_streams <= 0 || gops_per_stream <= 0 || gop_len <= 0) return fail(c, ICSP_ERR_PARAM, "bad stream geometry");
     if ((long long)n_streams * gops_per_stream * gop_len > c->cap) return fail(c, ICSP_ERR_CAPACITY, "more frames than capacity %d", c->cap);
     if ((long long)n_streams * gops_per_stream > 65535) return fail(c, ICSP_ERR_PARAM, "more than 65535 GOPs per call");
+    // chunks are whole streams and the entropy / parse kernels index the frames of a chunk with grid.y
+    const long long fps = (long long)gops_per_stream * gop_len;
+    if (fps > 65535) return fail(c, ICSP_ERR_PARAM, "more than 65535 frames per stream per call (split the stream at a GOP boundary)");
+    if ((n_streams + (65535 / fps) - 1) / (65535 / fps) > 64) return fail(c, ICSP_ERR_PARAM, "too many frames per call for 64 chunks of <= 65535 frames");
     return ICSP_OK;
 }
 
 // streams per chunk for the entropy path (chunks are whole streams)
-static int chunk_streams(const icsp_ctx* c, int n_streams, int gops_per_stream, bool pipelined)
+static int chunk_streams(const icsp_ctx* c, int n_streams, int gops_per_stream, int gop_len, bool pipelined)
 {
     const int cg = chunk_gops(c, n_streams * gops_per_stream, pipelined);
+    const long long fps = (long long)gops_per_stream * gop_len;
     int cs = std::max(1, cg / gops_per_stream);
+    while (cs > 1 && cs * fps > 65535) cs--;                 // the entropy kernels put the frame on grid.y
     while ((n_streams + cs - 1) / cs > MAX_EN_CHUNKS) cs++;
     return cs;
 }
@@ -794,7 +863,7 @@ int icsp_entropy_run(icsp_ctx* c, int n_streams, int gops_per_stream, int gop_le
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     if ((rc = entropy_alloc(c))) return rc;
-    const int cs = chunk_streams(c, n_streams, gops_per_stream, false);
+    const int cs = chunk_streams(c, n_streams, gops_per_stream, gop_len, false);
     c->en_chunks.clear();
     if ((rc = fork_streams(c))) return rc;
     for (int s0 = 0, i = 0; s0 < n_streams; s0 += cs, i++)
@@ -851,8 +920,8 @@ int icsp_bits_download(icsp_ctx* c, int n_streams, const icsp_bits_out* out)
     return icsp_sync(c);
 }
 
-int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
-                        const icsp_bits_out* out)
+static int icsp_encode_streams_impl(icsp_ctx* c, const uint8_t* frames, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
+                                    const icsp_bits_out* out)
 {
     int rc = check_streams(c, n_streams, gops_per_stream, gop_len);
     if (rc) return rc;
@@ -862,7 +931,7 @@ int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int g
     if ((rc = entropy_alloc(c))) return rc;
     const Geom& g = c->g;
     const int fps = gops_per_stream * gop_len;
-    const int cs = chunk_streams(c, n_streams, gops_per_stream, true);
+    const int cs = chunk_streams(c, n_streams, gops_per_stream, gop_len, true);
     const int nchunks = (n_streams + cs - 1) / cs;
     c->en_chunks.clear();
     // ICSP_TIMELINE=1: print, per chunk, when its upload / kernels / downloads finished (ms from the start of the call);
@@ -987,7 +1056,7 @@ int icsp_dec_download(icsp_ctx* c, int n, uint8_t* out)
     return ICSP_OK;
 }
 
-int icsp_decode_gops(icsp_ctx* c, const icsp_dec_in* in, int n_gops, int gop_len, int qdc, int qac, uint8_t* out)
+static int icsp_decode_gops_impl(icsp_ctx* c, const icsp_dec_in* in, int n_gops, int gop_len, int qdc, int qac, uint8_t* out)
 {
     int rc = check_run(c, n_gops, gop_len, qdc, qac);
     if (rc) return rc;
@@ -1095,6 +1164,27 @@ int icsp_idct8x8(icsp_ctx* c, const int32_t* blocks, int n, int table, double* o
     return icsp_sync(c);
 }
 
+int icsp_quant(icsp_ctx* c, const double* dct, int n, int qdc, int qac, int chroma, int32_t* levels, uint8_t* acflag)
+{
+    if (!c || !dct || !levels || n <= 0 || qdc <= 0 || qac <= 0) return fail(c, ICSP_ERR_PARAM, "icsp_quant: bad arguments");
+    CU(cudaSetDevice(c->device));
+    int rc = shim_reserve(c, (size_t)n * (64 * 12 + 1) + 64);
+    if (rc) return rc;
+    double* din = (double*)c->d_shim;
+    int32_t* dl = (int32_t*)(din + (size_t)n * 64);
+    uint8_t* da = (uint8_t*)(dl + (size_t)n * 64);
+    CU(cudaMemcpyAsync(din, dct, (size_t)n * 64 * 8, cudaMemcpyHostToDevice, c->stream));
+    {
+        LaunchScope ls(c, K_QUANT_SHIM);
+        quant8x8_kernel<<<(n + 3) / 4, 256, 0, c->stream>>>(din, dl, da, n, (unsigned)((0x80000000ull + qdc - 1) / qdc),
+                                                             (unsigned)((0x80000000ull + qac - 1) / qac), chroma);
+    }
+    CU(cudaMemcpyAsync(levels, dl, (size_t)n * 64 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (acflag) CU(cudaMemcpyAsync(acflag, da, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    return icsp_sync(c);
+}
+
 // ---- instrumentation -------------------------------------------------------------------------------------
 int icsp_set_profiling(icsp_ctx* c, int enabled)
 {
@@ -1139,8 +1229,8 @@ int icsp_configure(icsp_ctx* c, int n_compute_streams, int chunk_gops_)
 }
 
 // ---- decoder with the bit reader on the GPU ------------------------------------------------
-int icsp_decode_streams(icsp_ctx* c, const icsp_dec_bits_in* in, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
-                        uint8_t* out)
+static int icsp_decode_streams_impl(icsp_ctx* c, const icsp_dec_bits_in* in, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
+                                    uint8_t* out)
 {
     int rc = check_streams(c, n_streams, gops_per_stream, gop_len);
     if (rc) return rc;
@@ -1154,10 +1244,14 @@ int icsp_decode_streams(icsp_ctx* c, const icsp_dec_bits_in* in, int n_streams, 
     if (!c->d_rows) CU(cudaMalloc(&c->d_rows, (size_t)c->cap * g.mbh * sizeof(unsigned long long)));
     const int fps = gops_per_stream * gop_len;
     const size_t cap_bytes = (size_t)c->cap * en_frame_cap(g);
+    uint64_t prev_end = 0;
     for (int s = 0; s < n_streams; s++) {      // bodies in stream order, 4-byte aligned starts, inside the device region
         const uint64_t o = in->stream_offset[s], b = in->stream_bytes[s];
-        if ((o & 3) || o + b > cap_bytes || (s && o < in->stream_offset[s - 1] + in->stream_bytes[s - 1]))
-            return fail(c, ICSP_ERR_PARAM, "icsp_decode_streams: stream %d: offsets must ascend, be multiples of 4 and fit the context", s);
+        // written so that no sum can wrap: o <= cap, b <= cap - o; the previous stream's end was validated the same way
+        bool bad = (o & 3) || o > cap_bytes || b > cap_bytes - o;
+        if (!bad && s) bad = o < prev_end;
+        if (bad) return fail(c, ICSP_ERR_PARAM, "icsp_decode_streams: stream %d: offsets must ascend, be multiples of 4 and fit the context", s);
+        prev_end = o + b;
         for (int r = 0; r < fps * g.mbh; r++)
             if (in->row_bit_offset[(size_t)s * fps * g.mbh + r] > b * 8) return fail(c, ICSP_ERR_PARAM, "icsp_decode_streams: stream %d: row index beyond the body", s);
     }
@@ -1172,7 +1266,7 @@ int icsp_decode_streams(icsp_ctx* c, const icsp_dec_bits_in* in, int n_streams, 
     for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
     CU(cudaStreamWaitEvent(c->s_down, c->ev_fork, 0));
     // software pipeline over chunks of whole streams: H2D of bodies + row index | parse + reconstruction | D2H of the frames
-    const int cs = chunk_streams(c, n_streams, gops_per_stream, true);
+    const int cs = chunk_streams(c, n_streams, gops_per_stream, gop_len, true);
     for (int s0 = 0, i = 0; s0 < n_streams; s0 += cs, i++) {
         const int ns = std::min(cs, n_streams - s0);
         const size_t f0 = (size_t)s0 * fps, cnt = (size_t)ns * fps;
@@ -1232,6 +1326,37 @@ int icsp_event_elapsed_ms(icsp_ctx* c, int a, int b, float* ms)
     CU(cudaEventSynchronize(c->slots[b]));
     CU(cudaEventElapsedTime(ms, c->slots[a], c->slots[b]));
     return ICSP_OK;
+}
+
+// The pipelined one-shot calls enqueue asynchronous copies into CALLER buffers on several streams.  Whatever makes one of
+// them fail half way (a CUDA error, a capacity check), nothing may still be in flight when the error code is returned: the
+// caller is free to release or reuse its buffers at once.
+static int settle(icsp_ctx* c, int rc)
+{
+    if (rc != ICSP_OK && c) { cudaSetDevice(c->device); cudaDeviceSynchronize(); }
+    return rc;
+}
+int icsp_inter_frame(icsp_ctx* c, const uint8_t* cur, const uint8_t* prev_recon, int n, int qdc, int qac, const icsp_enc_out* out)
+{
+    return settle(c, icsp_inter_frame_impl(c, cur, prev_recon, n, qdc, qac, out));
+}
+int icsp_encode_gops(icsp_ctx* c, const uint8_t* frames, int n_gops, int gop_len, int qdc, int qac, const icsp_enc_out* out)
+{
+    return settle(c, icsp_encode_gops_impl(c, frames, n_gops, gop_len, qdc, qac, out));
+}
+int icsp_decode_gops(icsp_ctx* c, const icsp_dec_in* in, int n_gops, int gop_len, int qdc, int qac, uint8_t* out)
+{
+    return settle(c, icsp_decode_gops_impl(c, in, n_gops, gop_len, qdc, qac, out));
+}
+int icsp_encode_streams(icsp_ctx* c, const uint8_t* frames, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
+                        const icsp_bits_out* out)
+{
+    return settle(c, icsp_encode_streams_impl(c, frames, n_streams, gops_per_stream, gop_len, qdc, qac, out));
+}
+int icsp_decode_streams(icsp_ctx* c, const icsp_dec_bits_in* in, int n_streams, int gops_per_stream, int gop_len, int qdc, int qac,
+                        uint8_t* out)
+{
+    return settle(c, icsp_decode_streams_impl(c, in, n_streams, gops_per_stream, gop_len, qdc, qac, out));
 }
 
 }  // extern "C"

@@ -4,12 +4,20 @@
 //
 //   icspenc -i <name_cif.yuv> -n <frames> [-q Q | --qpdc D --qpac A] [--intraPeriod P] [-w W -h H]
 //           [--EnMultiThread T] [--gpus G] [--no-recon] [--psnr] [--index] [--quiet]
+//   icspenc --batch <list.txt> -n <frames> ...      N independent streams (one input path per line) in ONE process: the
+//           streams are sharded over the GPUs (--gpus), each GPU encodes waves of --wave streams (default 16) with one
+//           icsp_encode_streams call per wave — the batch shape bench.py measures — while the next wave is read and the
+//           previous one written by --io-threads file threads (double buffering: read -> pinned -> H2D | kernels | D2H ->
+//           write).  Outputs per stream: <prefix>_compCIF_<QDC>_<QAC>_<IP>.bin and <prefix>_test_yuv.yuv.
 //
 // Outputs, like the reference: <prefix>_compCIF_<QDC>_<QAC>_<IP>.bin (prefix = input name up to the first '_',
 // encoder_main.cpp:10-17) and test_yuv.yuv (reconstruction, ENC:6376-6421).  Unlike the reference's
 // --EnMultiThread mode, the bitstream is always written and tail frames (n % intraPeriod) are encoded.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <fstream>
+#include <future>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +39,8 @@ struct Options {
     bool index = false;         // --index: write <bin>.idx, the macroblock-row index icspdec uses to parse on the GPU
     bool psnr = false;          // --psnr: luma PSNR of the reconstruction, reduced on the GPU (what the reference's decoder logs, DEC.h:332-350)
     bool host_entropy = false;  // --host-entropy: download the syntax arrays and entropy-code on the CPU (round-1 path)
+    std::string batch;          // --batch <list>: many streams, one process
+    int wave = 16, io_threads = 0;
 };
 
 void help()
@@ -42,6 +52,8 @@ void help()
            "--qpdc : QP of DC\n--qpac : QP of AC\n--intraPeriod: period of intra frame(0: All intra)\n"
            "--EnMultiThread: host threads for the entropy coder (0 = all cores)\n"
            "--gpus: GPUs to shard the GOPs over (default 1)\n--no-recon: do not write test_yuv.yuv\n"
+           "--batch <list>: encode every stream listed in <list> (one path per line) in one process, sharded over the GPUs;\n"
+           "                --wave S streams per device call (default 16), --io-threads T file threads per GPU\n"
            "--host-entropy: entropy-code on the CPU instead of the GPU\n--psnr: print the average luma PSNR (computed on the GPU; works with --no-recon)\n--help : help message\n");
 }
 
@@ -64,6 +76,9 @@ int parse(int argc, char** argv, Options& o)
         else if (a == "--intraPeriod") { if (!val(o.ip)) return -1; }
         else if (a == "--EnMultiThread") { if (!val(o.threads)) return -1; }
         else if (a == "--gpus") { if (!val(o.gpus)) return -1; }
+        else if (a == "--batch") { if (i + 1 >= argc) return -1; o.batch = argv[++i]; }
+        else if (a == "--wave") { if (!val(o.wave)) return -1; }
+        else if (a == "--io-threads") { if (!val(o.io_threads)) return -1; }
         else if (a == "--no-recon") o.recon = false;
         else if (a == "--host-entropy") o.host_entropy = true;
         else if (a == "--psnr") o.psnr = true;
@@ -83,12 +98,204 @@ struct Shard {          // one GPU's contiguous range of GOPs
     std::vector<uint64_t> sse;  // --psnr: [frames][3]
     std::vector<std::vector<uint64_t>> rows;   // --index: per segment, [frames][mbh] bit offsets inside the segment
 };
+
+// ---- batch mode: N independent streams, one process ---------------------------------------------------------------------
+// parallel helper: run fn(i) for i in [0, n) on `threads` threads
+template <typename F>
+void parallel_for(int n, int threads, F fn)
+{
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < std::max(1, std::min(threads, n)); t++)
+        th.emplace_back([&] { for (int i = next++; i < n; i = next++) fn(i); });
+    for (auto& t : th) t.join();
+}
+
+std::string stream_prefix(const std::string& path)
+{
+    const size_t sl = path.find_last_of('/');
+    const std::string base = sl == std::string::npos ? path : path.substr(sl + 1);
+    const size_t us = base.find('_');
+    return us == std::string::npos ? base : base.substr(0, us);      // encoder_main.cpp:10-17: name up to the first '_'
+}
+
+int run_batch(const Options& o)
+{
+    std::vector<std::string> inputs;
+    {
+        std::ifstream f(o.batch);
+        if (!f) { fprintf(stderr, "[ERROR] cannot open %s\n", o.batch.c_str()); return 1; }
+        for (std::string line; std::getline(f, line);) {
+            while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+            if (!line.empty()) inputs.push_back(line);
+        }
+    }
+    const int S = (int)inputs.size();
+    if (S == 0) { fprintf(stderr, "[ERROR] %s lists no streams\n", o.batch.c_str()); return 1; }
+    const int n = o.frames, nmbh = o.height / 16;
+    const size_t fb = (size_t)o.width * o.height * 3 / 2;
+    const int gop = o.ip == 0 ? 1 : o.ip, full = n / gop, tail = n - full * gop;
+    const int G = std::max(1, std::min(o.gpus, S));
+    const int hw = std::max(1, (int)std::thread::hardware_concurrency());
+    const int io = o.io_threads > 0 ? o.io_threads : std::max(2, hw / G);
+    std::atomic<int> failed{0};
+    std::vector<std::string> errs(G);
+    const auto t0 = std::chrono::steady_clock::now();
+
+    auto gpu_thread = [&](int d) {
+        const int s_begin = (int)((long long)S * d / G), s_end = (int)((long long)S * (d + 1) / G);
+        const int mine = s_end - s_begin;
+        if (mine <= 0) return;
+        const int W = std::max(1, std::min(o.wave, mine));
+        auto bail = [&](const std::string& m) { errs[d] = m; failed++; };
+        icsp_ctx* ctx = nullptr;
+        if (icsp_create(&ctx, d, o.width, o.height, W * std::max(full * gop, tail))) return bail(icsp_last_error(nullptr));
+        // double buffers: frames in (write-combined pinned), reconstruction and bits out (pinned)
+        struct Buf { uint8_t *in = nullptr, *tail_in = nullptr, *rec = nullptr, *bits = nullptr; size_t bits_cap = 0;
+                     std::vector<uint64_t> nbits, off, tnbits, toff, rows, trows; uint8_t* tbits = nullptr; size_t tbits_cap = 0; int count = 0, first = 0; } buf[2];
+        for (auto& b : buf) {
+            b.in = (uint8_t*)icsp_host_alloc_upload((size_t)W * full * gop * fb + 64);
+            if (tail) b.tail_in = (uint8_t*)icsp_host_alloc_upload((size_t)W * tail * fb);
+            if (o.recon) b.rec = (uint8_t*)icsp_host_alloc((size_t)W * n * fb);
+            b.bits_cap = (size_t)W * full * gop * ((size_t)o.width * o.height + 32) + 64;
+            b.bits = (uint8_t*)icsp_host_alloc(b.bits_cap);
+            if (tail) { b.tbits_cap = (size_t)W * tail * ((size_t)o.width * o.height + 32) + 64; b.tbits = (uint8_t*)icsp_host_alloc(b.tbits_cap); }
+            if (!b.in || !b.bits || (o.recon && !b.rec) || (tail && (!b.tail_in || !b.tbits))) return bail("pinned host allocation failed");
+            b.nbits.resize(W); b.off.resize(W); b.tnbits.resize(W); b.toff.resize(W);
+        }
+        auto load = [&](Buf& b, int first, int count) {      // read `count` streams starting at stream `first` into b
+            b.first = first; b.count = count;
+            parallel_for(count, io, [&](int i) {
+                FILE* fi = fopen(inputs[first + i].c_str(), "rb");
+                bool ok = fi != nullptr;
+                if (ok && full) ok = fread(b.in + (size_t)i * full * gop * fb, fb, (size_t)full * gop, fi) == (size_t)full * gop;
+                if (ok && tail) ok = fread(b.tail_in + (size_t)i * tail * fb, fb, tail, fi) == (size_t)tail;
+                if (fi) fclose(fi);
+                if (!ok) { errs[d] = "cannot read " + std::to_string(n) + " frames from " + inputs[first + i]; failed++; }
+            });
+        };
+        auto encode = [&](Buf& b) -> int {
+            int rc = ICSP_OK;
+            if (full) {
+                // reconstruction layout of the call = [stream][full*gop frames]; the per-stream file is assembled when writing
+                icsp_bits_out bo{b.bits, b.bits_cap, b.nbits.data(), b.off.data(), o.recon ? b.rec : nullptr};
+                rc = icsp_encode_streams(ctx, b.in, b.count, full, gop, o.qdc, o.qac, &bo);
+                if (rc == ICSP_ERR_CAPACITY) {       // worst-case bound (noise at QP 1): grow the staging buffer once
+                    const size_t cap = icsp_bits_bound(o.width, o.height, b.count * full * gop);
+                    icsp_host_free(b.bits); b.bits = (uint8_t*)icsp_host_alloc(cap); b.bits_cap = b.bits ? cap : 0;
+                    if (!b.bits) return ICSP_ERR_NOMEM;
+                    icsp_bits_out bo2{b.bits, b.bits_cap, b.nbits.data(), b.off.data(), o.recon ? b.rec : nullptr};
+                    rc = icsp_encode_streams(ctx, b.in, b.count, full, gop, o.qdc, o.qac, &bo2);
+                }
+                if (!rc && o.index) { b.rows.resize((size_t)b.count * full * gop * nmbh); rc = icsp_bits_row_index(ctx, b.count * full * gop, b.rows.data()); }
+            }
+            if (!rc && tail) {
+                icsp_bits_out bo{b.tbits, b.tbits_cap, b.tnbits.data(), b.toff.data(), o.recon ? b.rec + (size_t)W * full * gop * fb : nullptr};
+                rc = icsp_encode_streams(ctx, b.tail_in, b.count, 1, tail, o.qdc, o.qac, &bo);
+                if (rc == ICSP_ERR_CAPACITY) {
+                    const size_t cap = icsp_bits_bound(o.width, o.height, b.count * tail);
+                    icsp_host_free(b.tbits); b.tbits = (uint8_t*)icsp_host_alloc(cap); b.tbits_cap = b.tbits ? cap : 0;
+                    if (!b.tbits) return ICSP_ERR_NOMEM;
+                    icsp_bits_out bo2{b.tbits, b.tbits_cap, b.tnbits.data(), b.toff.data(), o.recon ? b.rec + (size_t)W * full * gop * fb : nullptr};
+                    rc = icsp_encode_streams(ctx, b.tail_in, b.count, 1, tail, o.qdc, o.qac, &bo2);
+                }
+                if (!rc && o.index) { b.trows.resize((size_t)b.count * tail * nmbh); rc = icsp_bits_row_index(ctx, b.count * tail, b.trows.data()); }
+            }
+            return rc;
+        };
+        auto store = [&](Buf& b) {
+            parallel_for(b.count, io, [&](int i) {
+                const std::string prefix = stream_prefix(inputs[b.first + i]);
+                icsp_host::StreamParams sp;
+                sp.width = o.width; sp.height = o.height; sp.qp_dc = o.qdc; sp.qp_ac = o.qac; sp.intra_period = o.ip; sp.nframes = n;
+                icsp_host::BitString all;
+                if (full) all.append_msb_bytes(b.bits + b.off[i], b.nbits[i]);
+                if (tail) all.append_msb_bytes(b.tbits + b.toff[i], b.tnbits[i]);
+                std::vector<uint8_t> bin = icsp_host::stream_header(sp);
+                const std::vector<uint8_t> body = all.reference_body();
+                bin.insert(bin.end(), body.begin(), body.end());
+                char name[600];
+                snprintf(name, sizeof(name), "%s_compCIF_%d_%d_%d.bin", prefix.c_str(), o.qdc, o.qac, o.ip);
+                FILE* fo = fopen(name, "wb");
+                if (!fo || fwrite(bin.data(), 1, bin.size(), fo) != bin.size()) { errs[d] = std::string("cannot write ") + name; failed++; }
+                if (fo) fclose(fo);
+                if (o.index) {
+                    snprintf(name, sizeof(name), "%s_compCIF_%d_%d_%d.bin.idx", prefix.c_str(), o.qdc, o.qac, o.ip);
+                    FILE* fx = fopen(name, "wb");
+                    if (fx) {
+                        const uint32_t hdr[4] = {(uint32_t)o.width, (uint32_t)o.height, (uint32_t)n, (uint32_t)nmbh};
+                        fwrite("ICSPIDX1", 1, 8, fx); fwrite(hdr, 4, 4, fx);
+                        if (full) fwrite(b.rows.data() + (size_t)i * full * gop * nmbh, 8, (size_t)full * gop * nmbh, fx);
+                        if (tail) {
+                            std::vector<uint64_t> tr(b.trows.begin() + (size_t)i * tail * nmbh, b.trows.begin() + (size_t)(i + 1) * tail * nmbh);
+                            for (auto& v : tr) v += full ? b.nbits[i] : 0;
+                            fwrite(tr.data(), 8, tr.size(), fx);
+                        }
+                        fclose(fx);
+                    } else { errs[d] = std::string("cannot write ") + name; failed++; }
+                }
+                if (o.recon) {
+                    snprintf(name, sizeof(name), "%s_test_yuv.yuv", prefix.c_str());
+                    FILE* fr = fopen(name, "wb");
+                    bool ok = fr != nullptr;
+                    if (ok && full) ok = fwrite(b.rec + (size_t)i * full * gop * fb, fb, (size_t)full * gop, fr) == (size_t)full * gop;
+                    if (ok && tail) ok = fwrite(b.rec + (size_t)W * full * gop * fb + (size_t)i * tail * fb, fb, tail, fr) == (size_t)tail;
+                    if (fr) fclose(fr);
+                    if (!ok) { errs[d] = std::string("cannot write ") + name; failed++; }
+                }
+            });
+        };
+        // pipeline over waves: load(i+1) | encode(i) | store(i-1)
+        const int nwaves = (mine + W - 1) / W;
+        std::future<void> loading, storing;
+        load(buf[0], s_begin, std::min(W, mine));
+        for (int wv = 0; wv < nwaves && !failed; wv++) {
+            Buf& cur = buf[wv & 1];
+            Buf& nxt = buf[(wv + 1) & 1];
+            if (storing.valid()) storing.get();                      // nxt's outputs have been written
+            if (wv + 1 < nwaves) {
+                const int first = s_begin + (wv + 1) * W, count = std::min(W, s_end - first);
+                loading = std::async(std::launch::async, [&, first, count] { load(nxt, first, count); });
+            }
+            const int rc = encode(cur);
+            if (rc) { bail(std::string(icsp_last_error(ctx)) + " (code " + std::to_string(rc) + ")"); }
+            if (loading.valid()) loading.get();
+            if (!rc) storing = std::async(std::launch::async, [&] { store(cur); });
+        }
+        if (loading.valid()) loading.get();
+        if (storing.valid()) storing.get();
+        for (auto& b : buf) { icsp_host_free(b.in); icsp_host_free(b.tail_in); icsp_host_free(b.rec); icsp_host_free(b.bits); icsp_host_free(b.tbits); }
+        icsp_destroy(ctx);
+    };
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < G; d++) th.emplace_back(gpu_thread, d);
+        for (auto& t : th) t.join();
+    }
+    if (failed) {
+        for (int d = 0; d < G; d++) if (!errs[d].empty()) fprintf(stderr, "[ERROR] GPU %d: %s\n", d, errs[d].c_str());
+        return 1;
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!o.quiet)
+        fprintf(stderr, "icspenc: batch of %d streams x %d frames on %d GPU(s): %.3f s wall incl. file reads and writes (%.0f frames/s)\n", S, n, G, sec,
+                (double)S * n / sec);
+    return 0;
+}
 }  // namespace
 
 int main(int argc, char** argv)
 {
     Options o;
     if (parse(argc, argv, o)) return 1;
+    if (!o.batch.empty()) {
+        if (o.frames <= 0 || o.qdc <= 0 || o.qac <= 0 || o.ip < 0 || o.ip > 63 || (o.width & 15) || (o.height & 15) || o.qdc > 255 || o.qac > 255 ||
+            o.host_entropy || o.psnr) {
+            fprintf(stderr, "[ERROR] uncorrect parameters (--batch needs -n > 0, QP in 1..255, intraPeriod in 0..63; not with --host-entropy/--psnr)\n");
+            return 1;
+        }
+        return run_batch(o);
+    }
     if (o.input.empty() || o.frames <= 0 || o.qdc <= 0 || o.qac <= 0 || o.ip < 0 || o.ip > 63 || (o.width & 15) || (o.height & 15) ||
         o.qdc > 255 || o.qac > 255) {
         fprintf(stderr, "[ERROR] uncorrect parameters (need -i, -n > 0, QP in 1..255, intraPeriod in 0..63, width/height multiples of 16)\n");
@@ -150,7 +357,7 @@ int main(int argc, char** argv)
             const size_t f0 = (size_t)s.first_frame + (size_t)g * s.gop_len;
             if (o.host_entropy) {
                 icsp_enc_out out{levels + f0 * nmb * 384, acflag + f0 * nmb * 6, mpm + f0 * nmb * 4, ipm + f0 * nmb * 4,
-                                 mvd + f0 * nmb * 2, nullptr, nullptr, recon ? recon + f0 * fb : nullptr};
+                                 mvd + f0 * nmb * 2, nullptr, nullptr, recon ? recon + f0 * fb : nullptr, nullptr};
                 s.rc = icsp_encode_gops(ctx, frames + f0 * fb, ng, s.gop_len, o.qdc, o.qac, &out);
             } else {   // entropy coding + bit packing on the GPU: only bits (and the reconstruction) cross PCIe
                 // pinned staging buffer, reused by the shard's calls.  First sized like the reference's own buffer (width*height

@@ -61,6 +61,10 @@ typedef struct icsp_enc_out {     /* any pointer may be NULL: that array is not 
     int16_t* mv;
     int32_t* minsad;
     uint8_t* recon;
+    double* dct;       /* optional debug tap, f64 [n][nmb][6][64]: forward DCT output of every block (DCT_block / CDCT_block,
+                          ENC:2685-2749, 4338-4419), raster order inside a block, BEFORE the DC predictor is subtracted; the
+                          north_star's 1e-9 check of the floating-point intermediates reads it.  Honoured by icsp_encode_gops,
+                          icsp_intra_frame and icsp_inter_frame; 3 KB per macroblock, so keep n small. */
 } icsp_enc_out;
 
 typedef struct icsp_dec_in {      /* what the host bit reader parsed (DEC:38-404), same SoA layout */
@@ -170,6 +174,16 @@ int icsp_me_sad(icsp_ctx* ctx, const uint8_t* cur_y, const uint8_t* ref_y, int n
 int icsp_dct8x8(icsp_ctx* ctx, const int32_t* blocks, int n, double* out);
 /* IDCT_block (ENC:2825-2893 when table==0, DEC:3331-3445 when table==1): int32 [n][64] -> f64 [n][64] */
 int icsp_idct8x8(icsp_ctx* ctx, const int32_t* blocks, int n, int table, double* out);
+/* Quantization_block (ENC:2750-2824; chroma != 0: CQuantization_block ENC:4610-4656): f64 [n][64] in raster order ->
+ * int32 levels [n][64] (raster order, QstepDC at [0][0]) and acflag [n] (1 iff all 63 AC levels are zero; may be NULL) */
+int icsp_quant(icsp_ctx* ctx, const double* dct, int n, int qp_dc, int qp_ac, int chroma, int32_t* levels, uint8_t* acflag);
+/* intraPrediction (ENC:556-643) on n independent frames: same outputs as icsp_encode_gops with gop_len 1 */
+int icsp_intra_frame(icsp_ctx* ctx, const uint8_t* i420_frames, int n, int qp_dc, int qp_ac, const icsp_enc_out* out);
+/* interPrediction(cur, prev) (ENC:1986-2072) on n independent frame pairs: cur_i420[i] is coded against prev_recon_i420[i],
+ * the RECONSTRUCTION of its predecessor (prev.reconstructedY/Cb/Cr, ENC:2087,2176,2518-2520).  Outputs as in icsp_enc_out
+ * for the n current frames; needs a context of capacity >= 2*n frames. */
+int icsp_inter_frame(icsp_ctx* ctx, const uint8_t* cur_i420, const uint8_t* prev_recon_i420, int n, int qp_dc, int qp_ac,
+                     const icsp_enc_out* out);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* When enabled every kernel launch is bracketed by CUDA events on the context stream. */

@@ -23,3 +23,17 @@ $CXX -O2 -w -include cstring -include cmath -include cstdlib -include cstdio -o 
 # function-level tap harness: our harness TU + the three non-main encoder TUs
 $CXX -O2 -w -pthread -I"$ENC" -o "$OUT/ref_taps" "$HERE/ref_taps.cpp" "$ENC/ICSP_Codec_Encoder_source.cpp" "$ENC/ICSPCodec.cpp" "$ENC/ICSP_thread.cpp"
 echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')"
+# reference-side binding (integration/icsp_ref_shim.cpp): the reference's own main / loader / makebitstream / dump on top of
+# libicspcuda.  The reference's single_thread_encoding is renamed inside its own translation unit only (-D), every other
+# reference source is compiled as it is; the shim provides the replacement definition.
+ROOT="$(cd "$HERE/.." && pwd)"
+if [ -f "$ROOT/icspcodec_b200/libicspcuda.so" ]; then
+  $CXX -O2 -w -c -Dsingle_thread_encoding=ref_single_thread_encoding -o "$OUT/enc_source_renamed.o" "$ENC/ICSP_Codec_Encoder_source.cpp"
+  $CXX -O2 -w -pthread -I"$ENC" -I"$ROOT/include" -o "$OUT/ICSPCodec_gpu" "$ENC/encoder_main.cpp" "$ENC/ICSPCodec.cpp" "$ENC/ICSP_thread.cpp" \
+      "$OUT/enc_source_renamed.o" "$ROOT/integration/icsp_ref_shim.cpp" -L"$ROOT/icspcodec_b200" -licspcuda \
+      -Wl,-rpath,'$ORIGIN/../../icspcodec_b200' -Wl,-rpath,/root/repo/icspcodec_b200
+  rm -f "$OUT/enc_source_renamed.o"
+  echo "build_ref: built ICSPCodec_gpu (reference front end + writer on libicspcuda)"
+else
+  echo "build_ref: libicspcuda.so not built yet - skipping ICSPCodec_gpu" >&2
+fi

@@ -196,3 +196,17 @@ def ref_dct(blocks: np.ndarray, inverse: bool = False) -> np.ndarray:
         return np.fromfile(os.path.join(tmp, "out.bin"), np.float64).reshape(-1, 64)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def ref_quant(dct: np.ndarray, qdc: int, qac: int, chroma: bool):
+    """Quantization_block / CQuantization_block of the compiled reference on stand-alone blocks: (levels int32 [n][64], acflag int32 [n])."""
+    tmp = tempfile.mkdtemp(prefix="icspref_")
+    try:
+        d = np.ascontiguousarray(dct, np.float64).reshape(-1, 64)
+        d.tofile(os.path.join(tmp, "in.bin"))
+        subprocess.run([os.path.join(REF_DIR, "ref_taps"), "quant", "in.bin", str(qdc), str(qac), "1" if chroma else "0", "out.bin"], cwd=tmp, check=True)
+        o = np.fromfile(os.path.join(tmp, "out.bin"), np.int32)
+        n = d.shape[0]
+        return o[: n * 64].reshape(n, 64), o[n * 64:]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)

@@ -9,6 +9,8 @@
 //                                                            int32 [nframes][396][2] (I-frames: zeros)
 //   ref_taps dct  <in> <out>      in: int32 [n][64] residual blocks -> out: f64 [n][64]   (DCT_block)
 //   ref_taps idct <in> <out>      in: int32 [n][64] dequantised blocks -> out: f64 [n][64] (IDCT_block)
+//   ref_taps quant <in> <qdc> <qac> <chroma> <out>   in: f64 [n][64] DCT blocks -> out: int32 [n][64] levels + int32 [n] ACflag
+//                                                            (Quantization_block / CQuantization_block)
 //   ref_taps metime <in_yuv> <nframes> <reps>   time motionEstimation() alone, prints positions/s
 #include "ICSP_Codec_Encoder.h"
 #include <cstdio>
@@ -59,9 +61,52 @@ static int tap_dct(const char* in, const char* out, bool inverse)
     return 0;
 }
 
+static int tap_quant(const char* in, int qdc, int qac, int chroma, const char* out)
+{
+    FILE* f = fopen(in, "rb");
+    if (!f) { perror(in); return 2; }
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<double> v(sz / 8);
+    if (fread(v.data(), 8, v.size(), f) != v.size()) { perror("fread"); return 2; }
+    fclose(f);
+    const size_t n = v.size() / 64;
+    std::vector<int> lv(n * 64), ac(n);
+    for (size_t i = 0; i < n; i++) {
+        if (!chroma) {
+            BlockData bd;
+            memset(&bd, 0, sizeof(bd));
+            Block8d* dctp[4]; Block8i* qp[4];
+            bd.intraDCTblck = dctp; bd.intraQuanblck = qp;
+            dctp[0] = (Block8d*)malloc(sizeof(Block8d));     // Quantization_block frees its input (ENC:2795)
+            qp[0] = (Block8i*)malloc(sizeof(Block8i));
+            memcpy(dctp[0]->block, &v[i * 64], 64 * sizeof(double));
+            Quantization_block(bd, 0, 8, qdc, qac, INTRA);
+            memcpy(&lv[i * 64], qp[0]->block, 64 * sizeof(int));
+            ac[i] = bd.intraACflag[0];
+            free(qp[0]);
+        } else {
+            CBlockData bd;
+            memset(&bd, 0, sizeof(bd));
+            bd.intraDCTblck = (Block8d*)malloc(sizeof(Block8d));
+            bd.intraQuanblck = (Block8i*)malloc(sizeof(Block8i));
+            memcpy(bd.intraDCTblck->block, &v[i * 64], 64 * sizeof(double));
+            CQuantization_block(bd, 8, qdc, qac, INTRA);
+            memcpy(&lv[i * 64], bd.intraQuanblck->block, 64 * sizeof(int));
+            ac[i] = bd.intraACflag;
+            free(bd.intraQuanblck);
+        }
+    }
+    FILE* fo = fopen(out, "wb");
+    fwrite(lv.data(), sizeof(int), lv.size(), fo);
+    fwrite(ac.data(), sizeof(int), ac.size(), fo);
+    fclose(fo);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
-    if (argc < 2) { fprintf(stderr, "usage: ref_taps mv|dct|idct|metime ...\n"); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: ref_taps mv|dct|idct|quant|metime ...\n"); return 2; }
+    if (!strcmp(argv[1], "quant") && argc == 7) return tap_quant(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);
     if (!strcmp(argv[1], "dct") && argc == 4)  return tap_dct(argv[2], argv[3], false);
     if (!strcmp(argv[1], "idct") && argc == 4) return tap_dct(argv[2], argv[3], true);
 
@@ -101,6 +146,7 @@ int main(int argc, char** argv)
             for (int n = 1; n < nframes; n++) { motionEstimation(codec.frames[n], codec.frames[0]); calls++; }
         double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("{\"calls\": %ld, \"seconds\": %.6f, \"positions_per_s\": %.1f}\n", calls, s, calls * 396.0 * 64.0 / s);
+        fflush(stdout);   // _Exit does not flush, and stdout is fully buffered when it is a pipe
         _Exit(0);
     }
     fprintf(stderr, "bad arguments\n");

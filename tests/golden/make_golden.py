@@ -7,6 +7,8 @@ from the mount), so these fixtures are the pinned truth for every parity test:
   * ref_cases.json   md5 of clip / .bin / encoder recon / decoder YUV / full MVs per (clip, qp, ip) case
   * ref_small.npz    the first frames of one case in full (bin bytes, recon, decoder YUV, MVs)
   * ref_dct.npz      random residual / dequantised blocks with the reference's DCT_block / IDCT_block doubles
+  * ref_quant.npz    DCT blocks with the reference's Quantization_block / CQuantization_block levels and ACflags
+                     (python tests/golden/make_golden.py quant  regenerates only this file)
 """
 import hashlib
 import json
@@ -40,8 +42,29 @@ def md5(b) -> str:
     return hashlib.md5(bytes(b)).hexdigest()
 
 
+def make_quant():
+    rng = np.random.default_rng(2026)
+    res = rng.integers(-255, 256, size=(192, 64)).astype(np.int32)
+    res[:16] = rng.integers(-6, 7, size=(16, 64))
+    d = O.ref_dct(res)                                   # realistic coefficient statistics ...
+    d[32:64] = np.rint(d[32:64] * 2) / 2 - 0.5           # ... plus exact .5 ties on both sides of zero
+    d[64:72] = rng.integers(-40, 41, size=(8, 64)) * 8 - 0.5
+    d[72:80, 1:] = rng.uniform(-0.49, 0.49, size=(8, 63))   # ACflag == 1 blocks
+    z = dict(dct=d)
+    for qdc, qac in ((1, 1), (8, 8), (16, 16), (8, 3), (100, 255)):
+        for chroma in (0, 1):
+            lv, ac = O.ref_quant(d, qdc, qac, bool(chroma))
+            z[f"lv_{qdc}_{qac}_{chroma}"] = lv
+            z[f"ac_{qdc}_{qac}_{chroma}"] = ac.astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "ref_quant.npz"), **z)
+
+
 def main():
     assert O.have_ref(), "oracle/_ref missing: run oracle/build_ref.sh first"
+    if len(sys.argv) > 1 and sys.argv[1] == "quant":
+        make_quant()
+        return
+    make_quant()
     out = []
     for kind, seed, n, qdc, qac, ip in CASES:
         clip = synth.make_clip(kind, n, seed)

@@ -169,3 +169,82 @@ def test_icspenc_noise_at_qp1_exceeds_reference_buffer(tmp_path, oracle):
     assert len(want) > n * w * h                                   # the case really is beyond the reference's bound
     assert open(tmp_path / "noise_compCIF_1_1_2.bin", "rb").read() == want
     assert np.array_equal(np.fromfile(tmp_path / "test_yuv.yuv", np.uint8).reshape(n, -1), s.recon.reshape(n, -1))
+
+
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ICSPCodec_gpu")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/ICSPCodec_gpu not built (oracle/build_ref.sh needs /root/reference)")
+@pytest.mark.parametrize("case", [CASES[0], CASES[5], CASES[6], CASES[8], CASES[9]], ids=lambda c: f"{c['kind']}-q{c['qdc']}_{c['qac']}-ip{c['ip']}")
+def test_reference_front_end_on_libicspcuda(tmp_path, case):
+    """The reference-side binding, compiled (integration/icsp_ref_shim.cpp): the reference's OWN main, option parser, loader,
+    makebitstream and checkResultFrames linked against libicspcuda — only single_thread_encoding's per-frame calls are
+    replaced.  The reference's own writer must then produce the reference's own .bin and test_yuv.yuv, byte for byte."""
+    clip = synth.make_clip(case["kind"], case["nframes"], case["seed"])
+    clip.tofile(tmp_path / "clip_cif.yuv")
+    n, qdc, qac, ip = case["nframes"], case["qdc"], case["qac"], case["ip"]
+    subprocess.run([REF_GPU, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", str(ip)],
+                   cwd=tmp_path, check=True, stdout=subprocess.DEVNULL)
+    assert md5f(tmp_path / f"clip_compCIF_{qdc}_{qac}_{ip}.bin") == case["bin_md5"]
+    assert md5f(tmp_path / "test_yuv.yuv") == case["recon_md5"]
+
+
+def _gpu_count():
+    try:
+        return int(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.count("GPU "))
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_icspenc_batch(tmp_path, oracle, gpus):
+    """icspenc --batch: several streams in one process, one icsp_encode_streams call per wave (the shape bench.py measures),
+    tail frames (n % intraPeriod) included, double-buffered file IO; with --gpus 2 the streams are sharded over two devices.
+    Every stream's .bin / test_yuv.yuv / .idx equal the single-stream results of the oracle."""
+    if gpus > _gpu_count():
+        pytest.skip(f"needs {gpus} GPUs")
+    n, ip = 12, 5
+    kinds = [("highmotion", 301), ("flat", 7), ("akiyo", 9), ("highmotion", 302), ("intra", 12)]
+    names = []
+    for i, (k, seed) in enumerate(kinds):
+        synth.make_clip(k, n, seed).tofile(tmp_path / f"s{i}_cif.yuv")
+        names.append(f"s{i}_cif.yuv")
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    subprocess.run([ENC, "--batch", "list.txt", "-n", str(n), "-q", "8", "--intraPeriod", str(ip), "--gpus", str(gpus), "--wave", "2", "--index",
+                    "--quiet"], cwd=tmp_path, check=True)
+    for i, (k, seed) in enumerate(kinds):
+        clip = synth.make_clip(k, n, seed)
+        s = oracle.encode(clip, 352, 288, 8, 8, ip)
+        assert open(tmp_path / f"s{i}_compCIF_8_8_{ip}.bin", "rb").read() == oracle.write_bitstream(s, 352, 288, 8, 8, ip), f"stream {i}"
+        assert np.array_equal(np.fromfile(tmp_path / f"s{i}_test_yuv.yuv", np.uint8).reshape(n, -1), s.recon), f"stream {i}"
+        # the row index of the batch path drives the GPU bit reader of icspdec
+        subprocess.run([DEC, str(n), f"s{i}_compCIF_8_8_{ip}.bin", "8", "8", str(ip), "--out", f"dec{i}.yuv"], cwd=tmp_path, check=True,
+                       stderr=subprocess.DEVNULL)
+        ps, _ = oracle.parse_bitstream(open(tmp_path / f"s{i}_compCIF_8_8_{ip}.bin", "rb").read(), n)
+        assert np.array_equal(np.fromfile(tmp_path / f"dec{i}.yuv", np.uint8).reshape(n, -1), oracle.decode(ps, 352, 288, 8, 8, ip)), f"stream {i}"
+    # icspdec --batch: the same streams in one process, bit reader on the GPU (side-cars present), then on the host (--no-index)
+    (tmp_path / "bins.txt").write_text("\n".join(f"s{i}_compCIF_8_8_{ip}.bin" for i in range(len(kinds))) + "\n")
+    for extra in ([], ["--no-index"]):
+        subprocess.run([DEC, "--batch", "bins.txt", str(n), "--gpus", str(gpus), "--wave", "2"] + extra, cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+        for i in range(len(kinds)):
+            assert md5f(tmp_path / f"s{i}_compCIF_8_8_{ip}.bin.yuv") == md5f(tmp_path / f"dec{i}.yuv"), f"stream {i} {extra}"
+            os.remove(tmp_path / f"s{i}_compCIF_8_8_{ip}.bin.yuv")
+
+
+def test_icspenc_two_gpus_single_stream(tmp_path):
+    """icspenc --gpus 2 on one sequence: GOPs sharded over two devices, bit strings concatenated on the host (needs 2 GPUs)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = CASES[0]
+    clip = synth.make_clip(case["kind"], case["nframes"], case["seed"])
+    clip.tofile(tmp_path / "clip_cif.yuv")
+    n, qdc, qac = case["nframes"], case["qdc"], case["qac"]
+    subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", "3", "--gpus", "2", "--quiet"],
+                   cwd=tmp_path, check=True)
+    one = tmp_path / "one"
+    one.mkdir()
+    clip.tofile(one / "clip_cif.yuv")
+    subprocess.run([ENC, "-i", "clip_cif.yuv", "-n", str(n), "--qpdc", str(qdc), "--qpac", str(qac), "--intraPeriod", "3", "--gpus", "1", "--quiet"],
+                   cwd=one, check=True)
+    assert md5f(tmp_path / f"clip_compCIF_{qdc}_{qac}_3.bin") == md5f(one / f"clip_compCIF_{qdc}_{qac}_3.bin")
+    assert md5f(tmp_path / "test_yuv.yuv") == md5f(one / "test_yuv.yuv")

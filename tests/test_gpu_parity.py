@@ -99,7 +99,7 @@ def test_gop_batch_equals_sequential(gpu, oracle):
     res = gpu.encode_gops(frames, 6, 5, 8, 8)
     for g, c in enumerate(clips):
         s = oracle.encode(c, W, H, 8, 8, 5)
-        sub = type(res)(**{k: getattr(res, k)[g * 5:(g + 1) * 5] for k in res.__dataclass_fields__})
+        sub = type(res)(**{k: (None if getattr(res, k) is None else getattr(res, k)[g * 5:(g + 1) * 5]) for k in res.__dataclass_fields__})
         assert_syntax_equal(sub, s, what=f"gop {g}: ")
 
 
@@ -382,3 +382,93 @@ def test_gpu_bit_reader_stream_batch(oracle):
             ctx.decode_streams(np.frombuffer(bytes(blob), np.uint8), offs, lens, bad, ns, gps, gl, qdc, qac)
         bad = rows.copy(); bad[:, 1:] += np.uint64(3)
         ctx.decode_streams(np.frombuffer(bytes(blob), np.uint8), offs, lens, bad, ns, gps, gl, qdc, qac)
+
+
+# ---- BASELINE.json sizes: every config at its stated 300 frames (tests/golden/make_golden_full.py) ----------------------
+FULL = json.load(open(os.path.join(GOLD, "ref_cases_full.json")))
+
+
+@pytest.fixture(scope="module")
+def gpu300():
+    from icspcodec_b200 import IcspCuda
+    ctx = IcspCuda(W, H, max_frames=300)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", FULL, ids=lambda c: c["config"].split(",")[0].replace(" ", "_"))
+def test_baseline_configs_full_size(gpu300, case):
+    """configs[0], [1] (QP 1/8/16), [2], the first streams of [3] and [4] at 300 frames: the bitstream produced on the GPU,
+    the reconstruction and the decoded YUV (bit reader on the GPU, then dequant/IDCT/MC/recon) are byte-identical to what
+    the unmodified reference encoder / decoder wrote for the same input."""
+    n, qdc, qac, ip = case["nframes"], case["qdc"], case["qac"], case["ip"]
+    clip = synth.make_clip(case["kind"], n, case["seed"])
+    assert md5(clip.tobytes()) == case["clip_md5"]
+    data, recon, rows = gpu300.encode_sequence_bitstream(clip, qdc, qac, ip, want_recon=True, want_index=True)
+    assert len(data) == case["bin_len"]
+    assert md5(data) == case["bin_md5"]
+    assert md5(recon.tobytes()) == case["recon_md5"]
+    dec = gpu300.decode_sequence_bitstream(data, rows, n)
+    assert md5(dec.tobytes()) == case["dec_md5"]
+
+
+def test_batch_of_streams_full_size_matches_golden():
+    """configs[3] shape in one call: 4 streams x 300 frames (120 GOPs per launch, several pipelined chunks) — every stream's
+    body and reconstruction equal the reference's for that stream alone."""
+    from icspcodec_b200 import IcspCuda, finish_stream
+    cases = [c for c in FULL if c["config"].startswith("configs[3]")]
+    frames = np.concatenate([synth.make_clip(c["kind"], 300, c["seed"]) for c in cases], axis=0)
+    with IcspCuda(W, H, max_frames=frames.shape[0]) as ctx:
+        ctx.configure(4, 15)                                     # 8 chunks of 15 GOPs: exercises the chunked pipeline
+        bodies, sbits, recon = ctx.encode_streams(frames, len(cases), 30, 10, 8, 8, want_recon=True)
+        for s, c in enumerate(cases):
+            assert md5(finish_stream(bodies[s], int(sbits[s]), W, H, 8, 8, 10)) == c["bin_md5"], f"stream {s}"
+            assert md5(recon[s * 300:(s + 1) * 300].tobytes()) == c["recon_md5"], f"stream {s}"
+
+
+# ---- SURVEY 8(b) unit shims: icsp_quant, icsp_intra_frame, icsp_inter_frame, the DCT tap -------------------------------
+def test_quant_shim_matches_reference(gpu):
+    """Quantization_block / CQuantization_block of the compiled reference (tests/golden/ref_quant.npz: realistic coefficients,
+    exact .5 ties on both sides of zero, all-zero-AC blocks) for five quantiser pairs, luma (truncate) and chroma (floor)."""
+    z = np.load(os.path.join(GOLD, "ref_quant.npz"))
+    for qdc, qac in ((1, 1), (8, 8), (16, 16), (8, 3), (100, 255)):
+        for chroma in (0, 1):
+            lv, ac = gpu.quant(z["dct"], qdc, qac, bool(chroma))
+            assert np.array_equal(lv, z[f"lv_{qdc}_{qac}_{chroma}"]), (qdc, qac, chroma)
+            assert np.array_equal(ac, z[f"ac_{qdc}_{qac}_{chroma}"]), (qdc, qac, chroma)
+
+
+def test_intra_and_inter_frame_shims(gpu, oracle):
+    """icsp_intra_frame == intraPrediction on independent frames; icsp_inter_frame(cur, prev reconstruction) ==
+    interPrediction(cur, prev): every SoA output of the frame, against the oracle run on the same pair."""
+    clips = [synth.make_clip("highmotion", 2, 77), synth.make_clip("flat", 2, 7), synth.make_clip("akiyo", 2, 5)]
+    first = np.stack([c[0] for c in clips])
+    ri = gpu.intra_frame(first, 8, 16)
+    prev_recon, cur = [], []
+    for i, c in enumerate(clips):
+        s = oracle.encode(c, W, H, 8, 16, 2)
+        one = type(ri)(**{k: (None if getattr(ri, k) is None else getattr(ri, k)[i:i + 1]) for k in ri.__dataclass_fields__})
+        so = type(s)(**{k: (None if getattr(s, k) is None else getattr(s, k)[0:1]) for k in s.__dataclass_fields__})
+        assert_syntax_equal(one, so, what=f"intra {i}: ")
+        prev_recon.append(s.recon[0]); cur.append(c[1])
+    rp = gpu.inter_frame(np.stack(cur), np.stack(prev_recon), 8, 16)
+    for i, c in enumerate(clips):
+        s = oracle.encode(c, W, H, 8, 16, 2)
+        one = type(rp)(**{k: (None if getattr(rp, k) is None else getattr(rp, k)[i:i + 1]) for k in rp.__dataclass_fields__})
+        so = type(s)(**{k: (None if getattr(s, k) is None else getattr(s, k)[1:2]) for k in s.__dataclass_fields__})
+        assert_syntax_equal(one, so, what=f"inter {i}: ")
+
+
+def test_dct_tap_in_pipeline(gpu, oracle):
+    """The forward-DCT doubles INSIDE the encode pipeline (intra wavefront, inter luma, chroma of both frame types), through
+    the optional icsp_enc_out.dct tap, against the oracle's tap: within the north_star tolerance 1e-9 — and in fact 0 ulp."""
+    clip = synth.make_clip("highmotion", 4, 2024)
+    res = gpu.encode_gops(clip, 2, 2, 8, 8, with_dct=True)
+    for g in range(2):
+        s = oracle.encode(clip[2 * g:2 * g + 2], W, H, 8, 8, 2, with_dct=True)
+        got = res.dct[2 * g:2 * g + 2]
+        np.testing.assert_allclose(got, s.dct, rtol=1e-9, atol=1e-9)
+        assert np.array_equal(got, s.dct)
+    assert np.array_equal(res.recon[:2], oracle.encode(clip[:2], W, H, 8, 8, 2).recon)      # the tap changes nothing else
+    rp = gpu.inter_frame(clip[1:2], res.recon[0:1], 8, 8, with_dct=True)
+    assert np.array_equal(rp.dct[0], oracle.encode(clip[:2], W, H, 8, 8, 2, with_dct=True).dct[1])

@@ -79,3 +79,21 @@ def test_oracle_vs_live_reference(oracle):
     blocks = rng.integers(-255, 256, size=(32, 64)).astype(np.int32)
     assert np.array_equal(oracle.dct8x8(blocks), oracle.ref_dct(blocks))
     assert np.array_equal(oracle.idct8x8(blocks * 8, 0), oracle.ref_dct(blocks * 8, True))
+
+
+# ---- BASELINE.json sizes: 300-frame clips (tests/golden/make_golden_full.py) -------------------------------------------
+FULL = json.load(open(os.path.join(GOLD, "ref_cases_full.json")))
+
+
+@pytest.mark.parametrize("case", [FULL[0], FULL[5]], ids=lambda c: c["config"].split(",")[0].replace(" ", "_"))
+def test_oracle_matches_reference_at_baseline_size(oracle, case):
+    """configs[0] (akiyo-shaped, IP 10) and the flat/static configs[2] variant (thousands of zero-SAD early breaks, carried
+    spiral state over 290 inter frames) at the full 300 frames: .bin, reconstruction and decoder YUV md5 of the reference."""
+    clip = synth.make_clip(case["kind"], case["nframes"], case["seed"])
+    assert md5(clip.tobytes()) == case["clip_md5"]
+    s = oracle.encode(clip, W, H, case["qdc"], case["qac"], case["ip"])
+    bs = oracle.write_bitstream(s, W, H, case["qdc"], case["qac"], case["ip"])
+    assert len(bs) == case["bin_len"] and md5(bs) == case["bin_md5"]
+    assert md5(s.recon.tobytes()) == case["recon_md5"]
+    ps, _ = oracle.parse_bitstream(bs, case["nframes"])
+    assert md5(oracle.decode(ps, W, H, case["qdc"], case["qac"], case["ip"]).tobytes()) == case["dec_md5"]

@@ -5,7 +5,7 @@ import numpy as np
 from bench import make_batch, FB, NMB
 from icspcodec_b200 import IcspCuda
 streams, frames = 64, 300
-batch = make_batch(streams, frames, 0)
+batch = make_batch(streams, frames, 0, 8)
 n = batch.shape[0]
 ctx = IcspCuda(352, 288, max_frames=n)
 res = ctx.alloc_result(n, pinned=True)

@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo")
 import numpy as np
 from bench import make_batch, FB
 from icspcodec_b200 import IcspCuda, PinnedArray
-batch = make_batch(64, 300, 0); n = batch.shape[0]
+batch = make_batch(64, 300, 0, 8); n = batch.shape[0]
 ctx = IcspCuda(352, 288, max_frames=n)
 pin_in = PinnedArray((n, FB), np.uint8); pin_in.array[:] = batch
 pin_bits = PinnedArray((n * (352 * 288 + 32) + 64,), np.uint8)

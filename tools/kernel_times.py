@@ -11,7 +11,7 @@ cache = f"/tmp/icsp_batch_{S}_{F}.npy"
 if os.path.exists(cache):
     batch = np.load(cache, mmap_mode="r")
 else:
-    batch = make_batch(S, F, 0)
+    batch = make_batch(S, F, 0, 8)
     np.save(cache, batch)
 n = batch.shape[0]
 ctx = IcspCuda(352, 288, max_frames=n)

@@ -5,7 +5,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np
     from bench import make_batch
     from icspcodec_b200 import IcspCuda
-    batch = make_batch(64, 40, 0)
+    batch = make_batch(64, 40, 0, 8)
     n = batch.shape[0]
     ctx = IcspCuda(352, 288, max_frames=n)
     ctx.upload(batch)

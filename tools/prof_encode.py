@@ -17,7 +17,7 @@ ap.add_argument("--decode", action="store_true")
 ap.add_argument("--entropy", action="store_true")
 ap.add_argument("--bits-decode", action="store_true", help="encode_streams + row index + decode_streams (GPU bit reader)")
 a = ap.parse_args()
-batch = make_batch(a.streams, a.frames, 0)
+batch = make_batch(a.streams, a.frames, 0, 8)
 n = batch.shape[0]
 ctx = IcspCuda(352, 288, max_frames=n)
 ctx.upload(batch)

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from bench import make_batch
 from icspcodec_b200 import IcspCuda
-batch = make_batch(64, 300, 0)
+batch = make_batch(64, 300, 0, 8)
 n = batch.shape[0]
 ctx = IcspCuda(352, 288, max_frames=n)
 ctx.upload(batch); ctx.sync()
