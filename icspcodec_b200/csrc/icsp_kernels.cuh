@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(const __grid_constant__ G
     int32_t* rec = p.dcrec + (size_t)gop * nblk;
     int16_t* lvf = p.levels + f * g.nmb * 384;
     const bool chroma = warp > 0;
-    const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh, n = bw * bh;
+    const int bw = chroma ? g.mbw : g.bw, bh = chroma ? g.mbh : g.bh;
     const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
     const bool walker = warp < 3 && !(warp == 0 && st.intra);   // intra luma DCs are chained inside the wavefront kernel
     if (staged) {
@@ -244,27 +244,56 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(const __grid_constant__ G
         if (threadIdx.x < 3) dc2s[2 * (threadIdx.x == 0 ? 4 * g.nmb : 4 * g.nmb + threadIdx.x * (g.nmb + 1))] = 1024;   // sentinels: predictor of block (0,0)
         __syncthreads();
         if (walker) {
+            // Each lane owns ONE block row (rows are taken 32 at a time) and walks it left to right, one block per step, two
+            // steps behind the lane above (the UR dependency): at step w lane l codes block (w - 2l, r0 + l).  Its left
+            // neighbour is its own previous result (a register); U, UR and UL are the last three results of the lane above,
+            // fetched with three warp shuffles.  Nothing on the dependent path touches shared memory (the raw DC of the next
+            // block is prefetched one step ahead, results are stored fire-and-forget), so a step costs one shuffle + median +
+            // quantiser latency instead of a shared-memory round trip, index arithmetic and a warp barrier.
             const int base = chroma ? 4 * g.nmb + 1 + (warp - 1) * (g.nmb + 1) : 0;
             double* slot = slots + base;
             int* dc2 = dc2s + 2 * base;
-            for (int wv = 0; wv < nwaves; wv++) {
-                const int by_lo = max(0, (wv - (bw - 1) + 1) >> 1), by_hi = min(bh - 1, wv >> 1);
-                for (int by = by_lo + lane; by <= by_hi; by += 32) {
-                    const int bx = wv - 2 * by, i = by * bw + bx;
-                    // A.5 without divergent branches: the three neighbours whose median is the predictor (single-neighbour
-                    // cases repeat that neighbour; the first block reads the sentinel); med3 is a true median (ENC:3677-3679)
-                    const bool ur = chroma ? (bx != bw - 1) : ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1));
-                    int a = i - 1, b = i - bw, c = ur ? i - bw + 1 : i - bw - 1;
-                    if (by == 0) { a = bx == 0 ? n : i - 1; b = a; c = a; }
-                    else if (bx == 0) { a = b; c = b; }
-                    const int va = dc2[2 * a], vb = dc2[2 * b], vc = dc2[2 * c];
-                    const int P = max(min(va, vb), min(max(va, vb), vc));
-                    int L;
-                    if (decode) L = dc2[2 * i + 1];
-                    else L = quant_magic(__dsub_rn(slot[i], (double)P), st.magic_dc, chroma);   // DPCM_DC_block: D -= P, then quantise
-                    *(int2*)(dc2 + 2 * i) = make_int2(L * st.qdc + P, L);                      // IQuantization + IDPCM_DC_block
+            for (int r0 = 0; r0 < bh; r0 += 32) {
+                const int rows = min(32, bh - r0), by = r0 + lane;
+                const bool row_ok = lane < rows;
+                const int steps = (bw - 1) + 2 * (rows - 1) + 1;
+                int h1 = 0, h2 = 0, h3 = 0;                 // my results at bx-1, bx-2, bx-3 (h1 = left neighbour)
+                int bx = -2 * lane;
+                const int rowbase = by * bw;
+                double raw = 0.0;
+                int lvl = 0;
+                if (row_ok && bx == 0) { if (decode) lvl = dc2[2 * rowbase + 1]; else raw = slot[rowbase]; }
+                for (int w = 0; w < steps; w++, bx++) {
+                    // the lane above is one step ahead in x: its h1 is my UR, h2 my U, h3 my UL
+                    int ur_v = __shfl_up_sync(0xffffffffu, h1, 1), u_v = __shfl_up_sync(0xffffffffu, h2, 1), ul_v = __shfl_up_sync(0xffffffffu, h3, 1);
+                    const bool act = row_ok && bx >= 0 && bx < bw;
+                    if (lane == 0 && r0 > 0 && act) {       // first row of a later pass: the row above was stored by the previous pass
+                        const int* up = dc2 + 2 * (rowbase - bw + bx);
+                        u_v = up[0];
+                        ur_v = bx + 1 < bw ? up[2] : 0;
+                        ul_v = bx > 0 ? up[-2] : 0;
+                    }
+                    // prefetch the input of my next block (address known one step ahead)
+                    double raw_n = 0.0;
+                    int lvl_n = 0;
+                    if (row_ok && bx + 1 >= 0 && bx + 1 < bw) { if (decode) lvl_n = dc2[2 * (rowbase + bx + 1) + 1]; else raw_n = slot[rowbase + bx + 1]; }
+                    int res = 0;
+                    if (act) {
+                        // A.5 without divergent branches: the three neighbours whose median is the predictor (single-neighbour cases
+                        // repeat that neighbour); med3 is a true median (ENC:3677-3679)
+                        const bool ur = chroma ? (bx != bw - 1) : ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1));
+                        int a = h1, b = u_v, c = ur ? ur_v : ul_v;
+                        if (by == 0) { a = bx == 0 ? 1024 : h1; b = a; c = a; }
+                        else if (bx == 0) { a = b; c = b; }
+                        const int P = max(min(a, b), min(max(a, b), c));
+                        const int L = decode ? lvl : quant_magic(__dsub_rn(raw, (double)P), st.magic_dc, chroma);   // DPCM_DC_block: D -= P, then quantise
+                        res = L * st.qdc + P;                                                                      // IQuantization + IDPCM_DC_block
+                        *(int2*)(dc2 + 2 * (rowbase + bx)) = make_int2(res, L);
+                    }
+                    h3 = h2; h2 = h1; h1 = res;
+                    raw = raw_n; lvl = lvl_n;
                 }
-                __syncwarp();
+                __syncwarp();                               // the next pass reads this pass's last row from shared memory
             }
         } else if (warp == 3 && !st.intra && !decode) {
             const int16_t* mv = p.mv + f * g.nmb * 2;
@@ -693,17 +722,15 @@ __device__ __forceinline__ void me_stage(const Geom& g, const MeLayout& L, uint3
 
 // rows_per_cta macroblock rows per CTA (blockIdx.x = row group * nseg + segment): 1 for the speculative pass of
 // non-persistent builds, mbh for the fixup pass, so that the usual "nothing to fix" launch is G*nseg cheap CTAs.
-__global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fixup, int rows_per_cta)
+__device__ __forceinline__ void me_search_rows(const Geom& g, const MeLayout& L, const FramePtrs& p, const Step& st, int gop, int seg, int fixup,
+                                               int row_begin, int row_end, unsigned char* s_me)
 {
-    extern __shared__ __align__(16) unsigned char s_me[];
-    const int gop = blockIdx.y, rg = blockIdx.x / L.nseg, seg = blockIdx.x - rg * L.nseg;
-    if (fixup && p.meflag[gop] == 0) return;
     const int m0 = seg * L.seg_mbs, nmbs = min(L.seg_mbs, g.mbw - m0);
     const size_t f = (size_t)gop * st.gop_len + st.t;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* s_win = (uint32_t*)s_me;
     uint8_t* s_cur = s_me + (size_t)(4 * L.copy_w + 8) * 4;
-  for (int mby = rg * rows_per_cta; mby < min(g.mbh, (rg + 1) * rows_per_cta); mby++) {
+  for (int mby = row_begin; mby < row_end; mby++) {
     const uint8_t* states = p.mestate + (size_t)gop * g.nmb + mby * g.mbw + m0;
     if (fixup) {
         int any = 0;
@@ -764,6 +791,85 @@ __global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePt
     }
     __syncthreads();   // the next row restages the window
   }
+}
+__global__ void __launch_bounds__(704) me_sad_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fixup, int rows_per_cta)
+{
+    extern __shared__ __align__(16) unsigned char s_me[];
+    const int gop = blockIdx.y, rg = blockIdx.x / L.nseg, seg = blockIdx.x - rg * L.nseg;
+    if (fixup && p.meflag[gop] == 0) return;
+    me_search_rows(g, L, p, st, gop, seg, fixup, rg * rows_per_cta, min(g.mbh, (rg + 1) * rows_per_cta), s_me);
+}
+
+// Exact fallback, pass 1: for frames where some search broke early, find for every macroblock and every one of
+// the 8 possible start states which visits have SAD == 0 (block identical to the candidate).  The break point
+// of a search depends only on these masks, never on non-zero SAD values.
+__device__ __forceinline__ void me_zero_rows(const Geom& g, const MeLayout& L, const FramePtrs& p, const Step& st, int gop, int seg, unsigned char* s_me)
+{
+    const int m0 = seg * L.seg_mbs, nmbs = min(L.seg_mbs, g.mbw - m0);
+    const size_t f = (size_t)gop * st.gop_len + st.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* s_win = (uint32_t*)s_me;
+    uint8_t* s_cur = s_me + (size_t)(4 * L.copy_w + 8) * 4;
+  for (int mby = 0; mby < g.mbh; mby++) {
+    me_stage<false>(g, L, s_win, s_cur, p.cur + f * g.fb, p.rec + (f - 1) * g.fb, mby, m0, nmbs);
+    const int mbl = warp;
+    if (warp < nmbs)
+    for (int state = 0; state < 8; state++) {
+        unsigned long long z = 0;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int idx = lane + 32 * h2;
+            const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
+            const int col = mbl * 16 + 16 + dx;
+            const uint32_t* wrow = s_win + (16 + dy) * L.pitch_w + (col >> 2);
+            const int sh = (col & 3) * 8;
+            const uint32_t* crow = (const uint32_t*)(s_cur + mbl * 16);
+            uint32_t diff = 0;
+            for (int j = 0; j < 16 && diff == 0; j++) {   // early out on the first differing row
+                const uint32_t w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3], w4 = wrow[4];
+                diff |= __funnelshift_r(w0, w1, sh) ^ crow[0];
+                diff |= __funnelshift_r(w1, w2, sh) ^ crow[1];
+                diff |= __funnelshift_r(w2, w3, sh) ^ crow[2];
+                diff |= __funnelshift_r(w3, w4, sh) ^ crow[3];
+                wrow += L.pitch_w;
+                crow += L.seg_mbs * 4;
+            }
+            z |= (unsigned long long)__ballot_sync(0xffffffffu, diff == 0) << (32 * h2);
+        }
+        if (lane == 0) p.mezero[((size_t)gop * g.nmb + mby * g.mbw + m0 + mbl) * 8 + state] = z;
+    }
+    __syncthreads();   // the next row restages the window
+  }
+}
+__global__ void __launch_bounds__(704) me_zero_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
+{   // grid (nseg, G): one CTA per frame segment walks all macroblock rows (it exits at once for unflagged frames)
+    extern __shared__ __align__(16) unsigned char s_me[];
+    if (p.meflag[blockIdx.y] == 0) return;
+    me_zero_rows(g, L, p, st, blockIdx.y, blockIdx.x, s_me);
+}
+
+// Exact fallback, pass 2: resolve the carried spiral state of every macroblock of a flagged frame.  A search
+// started in state s makes m = (index of its second zero-SAD visit)+1 moves, or 64; the state handed to the next
+// macroblock is c_next[s][m] (ENC:2094-2095: flag/xflag/yflag are initialised once per frame, never per MB).
+__device__ __forceinline__ void me_chain_walk(const Geom& g, const FramePtrs& p, int gop)
+{   // one thread
+    const unsigned long long* zm = p.mezero + (size_t)gop * g.nmb * 8;
+    uint8_t* states = p.mestate + (size_t)gop * g.nmb;
+    int s = 0;
+    for (int mb = 0; mb < g.nmb; mb++) {
+        states[mb] = (uint8_t)s;
+        const unsigned long long z = zm[mb * 8 + s];
+        int m = 64;
+        if (__popcll(z) >= 2) m = __ffsll((long long)(z & (z - 1)));
+        s = c_next[s][m];
+    }
+}
+__global__ void __launch_bounds__(32) me_chain_kernel(Geom g, FramePtrs p)
+{
+    const int gop = blockIdx.x;
+    if (p.meflag[gop] == 0) return;
+    if (threadIdx.x != 0) return;
+    me_chain_walk(g, p, gop);
 }
 
 // ---- persistent variant of the speculative (state 0) search ------------------------------------------------------
@@ -828,10 +934,17 @@ __device__ __forceinline__ void me_task_store(const MeLayout& L, uint32_t* s_win
 // CPITCH / CSEG: compile-time copies of L.pitch_w / L.seg_mbs (0 = use the runtime values).  With constants every
 // shared-memory address of the inner loop is base + immediate, which removes the per-row pointer arithmetic.
 // (704, 1): one CTA per SM by shared memory anyway, so let the compiler use up to 93 registers to keep more loads in flight
+// `fused` (frames of one segment, nseg == 1): the CTA that searched the frame also knows whether any of its searches broke
+// early, so it runs the exact carried-state fallback (zero masks -> chain -> re-search) itself, in the shared memory it
+// already owns.  The three fallback kernels then never have to be launched: as separate launches of 704-thread, 142 KB CTAs
+// they could only be scheduled once a whole SM had drained, and cost each chunk 0.3-0.5 ms of dead time per step although
+// they exit at once on natural content (profiles/README.md, round 2).
 template <int CPITCH, int CSEG>
-__global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
+__global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fused)
 {
     extern __shared__ __align__(16) unsigned char s_me[];
+    __shared__ unsigned s_breaks;
+    if (threadIdx.x == 0) s_breaks = 0;
     const int pitch_w = CPITCH ? CPITCH : L.pitch_w, seg_mbs = CSEG ? CSEG : L.seg_mbs;
     const int gop = blockIdx.y, seg = blockIdx.x;
     const int m0 = seg * seg_mbs, nmbs = min(seg_mbs, g.mbw - m0);
@@ -904,7 +1017,7 @@ __global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L
                 *(int*)(p.mv + (f * g.nmb + mb) * 2) = ((-wdx) & 0xffff) | ((-wdy) << 16);
                 p.minsad[f * g.nmb + mb] = (int32_t)best;
                 p.memoves[(size_t)gop * g.nmb + mb] = (uint8_t)moves;
-                if (moves < 64) atomicAdd(&p.meflag[gop], 1u);
+                if (moves < 64) { if (fused) atomicAdd(&s_breaks, 1u); else atomicAdd(&p.meflag[gop], 1u); }
             }
         }
         // (3) hand the prefetched rows over; narrow segments (fewer than 16 warps) fetch the rest without overlap
@@ -916,71 +1029,15 @@ __global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L
         }
         __syncthreads();
     }
-}
-
-// Exact fallback, pass 1: for frames where some search broke early, find for every macroblock and every one of
-// the 8 possible start states which visits have SAD == 0 (block identical to the candidate).  The break point
-// of a search depends only on these masks, never on non-zero SAD values.
-__global__ void __launch_bounds__(704) me_zero_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
-{   // grid (nseg, G): one CTA per frame segment walks all macroblock rows (it exits at once for unflagged frames)
-    extern __shared__ __align__(16) unsigned char s_me[];
-    const int gop = blockIdx.y, seg = blockIdx.x;
-    if (p.meflag[gop] == 0) return;
-    const int m0 = seg * L.seg_mbs, nmbs = min(L.seg_mbs, g.mbw - m0);
-    const size_t f = (size_t)gop * st.gop_len + st.t;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* s_win = (uint32_t*)s_me;
-    uint8_t* s_cur = s_me + (size_t)(4 * L.copy_w + 8) * 4;
-  for (int mby = 0; mby < g.mbh; mby++) {
-    me_stage<false>(g, L, s_win, s_cur, p.cur + f * g.fb, p.rec + (f - 1) * g.fb, mby, m0, nmbs);
-    const int mbl = warp;
-    if (warp < nmbs)
-    for (int state = 0; state < 8; state++) {
-        unsigned long long z = 0;
-#pragma unroll
-        for (int h2 = 0; h2 < 2; h2++) {
-            const int idx = lane + 32 * h2;
-            const int dx = c_cand[state][idx][0], dy = c_cand[state][idx][1];
-            const int col = mbl * 16 + 16 + dx;
-            const uint32_t* wrow = s_win + (16 + dy) * L.pitch_w + (col >> 2);
-            const int sh = (col & 3) * 8;
-            const uint32_t* crow = (const uint32_t*)(s_cur + mbl * 16);
-            uint32_t diff = 0;
-            for (int j = 0; j < 16 && diff == 0; j++) {   // early out on the first differing row
-                const uint32_t w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3], w4 = wrow[4];
-                diff |= __funnelshift_r(w0, w1, sh) ^ crow[0];
-                diff |= __funnelshift_r(w1, w2, sh) ^ crow[1];
-                diff |= __funnelshift_r(w2, w3, sh) ^ crow[2];
-                diff |= __funnelshift_r(w3, w4, sh) ^ crow[3];
-                wrow += L.pitch_w;
-                crow += L.seg_mbs * 4;
-            }
-            z |= (unsigned long long)__ballot_sync(0xffffffffu, diff == 0) << (32 * h2);
-        }
-        if (lane == 0) p.mezero[((size_t)gop * g.nmb + mby * g.mbw + m0 + mbl) * 8 + state] = z;
-    }
-    __syncthreads();   // the next row restages the window
-  }
-}
-
-// Exact fallback, pass 2: resolve the carried spiral state of every macroblock of a flagged frame.  A search
-// started in state s makes m = (index of its second zero-SAD visit)+1 moves, or 64; the state handed to the next
-// macroblock is c_next[s][m] (ENC:2094-2095: flag/xflag/yflag are initialised once per frame, never per MB).
-__global__ void __launch_bounds__(32) me_chain_kernel(Geom g, FramePtrs p)
-{
-    const int gop = blockIdx.x;
-    if (p.meflag[gop] == 0) return;
-    if (threadIdx.x != 0) return;
-    const unsigned long long* zm = p.mezero + (size_t)gop * g.nmb * 8;
-    uint8_t* states = p.mestate + (size_t)gop * g.nmb;
-    int s = 0;
-    for (int mb = 0; mb < g.nmb; mb++) {
-        states[mb] = (uint8_t)s;
-        const unsigned long long z = zm[mb * 8 + s];
-        int m = 64;
-        if (__popcll(z) >= 2) m = __ffsll((long long)(z & (z - 1)));
-        s = c_next[s][m];
-    }
+    if (!fused) return;
+    const unsigned breaks = s_breaks;           // the loop's last __syncthreads() ordered every increment before this read
+    if (threadIdx.x == 0) p.meflag[gop] = breaks;
+    if (breaks == 0) return;                    // natural content: the speculative state-0 search is the answer
+    me_zero_rows(g, L, p, st, gop, seg, s_me);  // which visits have SAD 0, for all 8 start states
+    __syncthreads();
+    if (threadIdx.x == 0) me_chain_walk(g, p, gop);   // start state of every macroblock
+    __syncthreads();
+    me_search_rows(g, L, p, st, gop, seg, 1, 0, g.mbh, s_me);   // re-search the macroblocks whose start state is not 0
 }
 
 // ---- unit shims ------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ const char* const kKernelNames[K_COUNT] = {
     "idct_recon_kernel<enc>(intra)", "idct_recon_kernel<dec>(intra)", "plane_sse_kernel", "row_index_kernel", "parse_rows_kernel",
     "quant8x8_kernel"};
 
-struct Pending { int k; cudaEvent_t a, b; };
+struct Pending { int k; cudaEvent_t a, b; cudaStream_t s; };
 
 }  // namespace
 
@@ -67,6 +67,7 @@ struct icsp_ctx {
     size_t shim_bytes = 0;
     double* d_dct_tap = nullptr;              // debug tap of the forward DCT (only while icsp_encode_gops_tap runs)
     bool tr_v1 = false;                       // ICSP_TR_V1=1: first-generation transform kernels (A/B comparisons)
+    int skew = 0;                             // ICSP_SKEW: pipeline stage (4*step + stage + 1) after which the next chunk may start; 0 = off
     // entropy coder (allocated on first use)
     uint32_t* d_blkbits = nullptr;
     unsigned long long *d_framebits = nullptr, *d_streambits = nullptr, *d_streamoff = nullptr, *d_chunktotal = nullptr;
@@ -88,6 +89,7 @@ struct icsp_ctx {
     char err[256] = "";
     size_t me_smem = 0, me_frame_smem = 0, intra_smem = 0, chain_smem = 0;
     bool me_persistent = true;
+    bool me_fused = true;                     // ICSP_ME_FUSED=0: exact carried-state fallback as three separate launches (A/B)
     int chain_staged = 1;
     unsigned char* d_intra_edges = nullptr;   // HD frames: per-GOP edge/DC/mode maps of the intra wavefront in global memory
     size_t intra_edge_stride = 0;
@@ -216,9 +218,17 @@ void fold_pending(icsp_ctx* c)
 {
     if (c->pending.empty()) return;
     cudaDeviceSynchronize();
+    static const bool dump = getenv("ICSP_KERNEL_TIMELINE") != nullptr;   // start/end of every launch relative to the first one (tools/kernel_timeline.py)
     for (auto& p : c->pending) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, p.a, p.b);
+        if (dump) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, c->pending.front().a, p.a);
+            int sid = -1;
+            for (int i = 0; i < MAX_CSTREAMS; i++) { if (c->cstream[i] == p.s) sid = i; if (c->hstream[i] == p.s) sid = 100 + i; }
+            fprintf(stderr, "[icsp kt] %-40s stream %3d start %9.4f end %9.4f\n", kKernelNames[p.k], sid, t0, t0 + ms);
+        }
         c->total_ms[p.k] += ms;
         c->free_events.push_back(p.a);
         c->free_events.push_back(p.b);
@@ -237,7 +247,7 @@ struct LaunchScope {
     }
     ~LaunchScope()
     {
-        if (c->profiling) { cudaEventRecord(b, s); c->pending.push_back({k, a, b}); }
+        if (c->profiling) { cudaEventRecord(b, s); c->pending.push_back({k, a, b, s}); }
     }
 };
 
@@ -328,33 +338,43 @@ void launch_fdct2(const Geom& g, const FramePtrs& p, const Step& st, dim3 grid, 
 int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream_t s)
 {
     const Geom& g = c->g;
-    CU(cudaMemsetAsync(p.meflag, 0, sizeof(uint32_t) * G, s));
-    CU(cudaMemsetAsync(p.mestate, 0, (size_t)G * g.nmb, s));
     const MeLayout& L = c->me;
     dim3 grid(g.mbh * L.nseg, G);
     const int threads = L.seg_mbs * 32;
+    // one CTA per frame (a frame is one segment): the frame kernel runs the exact fallback itself, no flags to clear, no
+    // further launches
+    const bool fused = c->me_persistent && L.nseg == 1 && c->me_fused;
+    if (!fused) {
+        CU(cudaMemsetAsync(p.meflag, 0, sizeof(uint32_t) * G, s));
+        CU(cudaMemsetAsync(p.mestate, 0, (size_t)G * g.nmb, s));
+    }
     {
         LaunchScope ls(c, K_ME_SAD, s);
         if (c->me_persistent && L.pitch_w == 104 && L.seg_mbs == 22)   // CIF: compile-time pitch / segment width
-            me_sad_frame_kernel<104, 22><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
-        else if (c->me_persistent) me_sad_frame_kernel<0, 0><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
+            me_sad_frame_kernel<104, 22><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st, fused ? 1 : 0);
+        else if (c->me_persistent) me_sad_frame_kernel<0, 0><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st, fused ? 1 : 0);
         else me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0, 1);
     }
+    if (fused) return ICSP_OK;
     { LaunchScope ls(c, K_ME_ZERO, s); me_zero_kernel<<<dim3(L.nseg, G), threads, c->me_smem, s>>>(g, L, p, st); }
     { LaunchScope ls(c, K_ME_CHAIN, s); me_chain_kernel<<<G, 32, 0, s>>>(g, p); }
     { LaunchScope ls(c, K_ME_FIXUP, s); me_sad_kernel<<<dim3(L.nseg, G), threads, c->me_smem, s>>>(g, L, p, st, 1, g.mbh); }
     return ICSP_OK;
 }
 
-// every step of GOPs [g0, g0+G) on stream s
 // one step (intra-GOP frame index st.t) of GOPs [g0, g0+G) on stream s
-int encode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, cudaStream_t s)
+int encode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, cudaStream_t s, cudaEvent_t signal = nullptr, int signal_stage = -1)
 {
+    auto stage_done = [&](int stage) { if (signal && stage == signal_stage) cudaEventRecord(signal, s); };
     const Geom& g = c->g;
     const int per = TR_THREADS / 8;
     dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
     const bool v1 = c->tr_v1 && !p.dct_tap;   // the DCT tap exists in the second-generation kernels only
-    if (st.intra) {
+    static const char* exp_skip = getenv("ICSP_EXP_SKIP");   // timing experiments only (results are wrong): "chain", "intra", "me"
+    const bool skip_chain = exp_skip && strstr(exp_skip, "chain"), skip_intra = exp_skip && strstr(exp_skip, "intra"), skip_me = exp_skip && strstr(exp_skip, "me");
+    if (st.intra && skip_intra) {
+    } else if (!st.intra && skip_me) {
+    } else if (st.intra) {
         int hi;
         cudaStream_t h = hi_begin(c, s, hi);
         { LaunchScope ls(c, K_INTRA_ENC, h);
@@ -364,34 +384,48 @@ int encode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, 
         const int rc = launch_me(c, p, st, G, s);
         if (rc) return rc;
     }
+    stage_done(0);
     {
         LaunchScope ls(c, st.intra ? K_FDCT_C : K_FDCT, s);
         if (v1) fdct_quant_kernel<<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
         else launch_fdct2(g, p, st, lgrid, s);
     }
-    {
+    stage_done(1);
+    if (!skip_chain) {
         int hi;
         cudaStream_t h = hi_begin(c, s, hi);
         { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 0, c->chain_staged); }
         hi_end(c, s, hi);
     }
+    stage_done(2);
     {
         LaunchScope ls(c, st.intra ? K_IDCT_ENC_C : K_IDCT_ENC, s);
         if (v1) idct_recon_kernel<0><<<lgrid, TR_THREADS, 0, s>>>(g, p, st);
         else if (st.intra) idct_recon_kernel2<0, true><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
         else idct_recon_kernel2<0, false><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
     }
+    stage_done(3);
     return ICSP_OK;
 }
 
 // every step of GOPs [g0, g0+G) on stream s
-int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+// Chunks of one call run the same kernel sequence on equal work, so left alone they march in lock step: all in their
+// latency-bound kernels (intra wavefront, DC chains) at the same time, then all in ME, ... and nothing overlaps.  `wait`
+// (recorded by the previous chunk once it is `skew` stages into its pipeline) holds this chunk back at its start, so that
+// the chunks stay out of phase: one chunk's latency-bound kernels then run underneath another's throughput kernels.
+int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s, cudaEvent_t wait = nullptr, cudaEvent_t signal = nullptr,
+                 int skew = 0)
 {
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
+    if (wait) CU(cudaStreamWaitEvent(s, wait, 0));
+    bool signalled = false;
     for (int t = 0; t < gop_len; t++) {
-        const int rc = encode_step(c, p, make_step(gop_len, t, qdc, qac), g0, G, s);
+        const bool here = signal && skew > 0 && (skew - 1) / 4 == t;
+        const int rc = encode_step(c, p, make_step(gop_len, t, qdc, qac), g0, G, s, here ? signal : nullptr, here ? (skew - 1) % 4 : -1);
         if (rc) return rc;
+        signalled |= here;
     }
+    if (signal && !signalled) CU(cudaEventRecord(signal, s));
     return ICSP_OK;
 }
 
@@ -586,7 +620,9 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     c->me_frame_smem = me_frame_smem_bytes(c->me);
     if (const char* e = getenv("ICSP_ME_SMEM_MIN")) c->me_frame_smem = std::max(c->me_frame_smem, (size_t)atoi(e));   // experiments: cap ME CTAs per SM
     if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
+    if (const char* e = getenv("ICSP_ME_FUSED")) c->me_fused = atoi(e) != 0;
     if (const char* e = getenv("ICSP_TR_V1")) c->tr_v1 = atoi(e) != 0;
+    if (const char* e = getenv("ICSP_SKEW")) c->skew = std::max(0, atoi(e));
     c->intra_smem = intra_smem_bytes(g);
     c->chain_smem = (size_t)(6 * g.nmb + 3) * 8 + 32;  // staged: one 8-byte slot per block + a sentinel per plane
     if (c->chain_smem > 100 * 1024) { c->chain_staged = 0; c->chain_smem = (size_t)6 * g.nmb * sizeof(int) + 32; }
@@ -608,9 +644,9 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
         }
         CUB(cudaFuncSetAttribute(me_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         CUB(cudaFuncSetAttribute(me_zero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<104, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        if ((size_t)optin < c->me_frame_smem) c->me_persistent = false;
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));     // it also has a few static bytes
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<104, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        if ((size_t)optin - 1024 < c->me_frame_smem) c->me_persistent = false;
         CUB(cudaFuncSetAttribute(intra_luma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
         CUB(cudaFuncSetAttribute(intra_luma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
         CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -691,7 +727,8 @@ int icsp_enc_run(icsp_ctx* c, int n_gops, int gop_len, int qdc, int qac)
     const int cg = chunk_gops(c, n_gops, false);
     if ((rc = fork_streams(c))) return rc;
     for (int g0 = 0, i = 0; g0 < n_gops; g0 += cg, i++)
-        if ((rc = encode_chunk(c, g0, std::min(cg, n_gops - g0), gop_len, qdc, qac, c->cstream[i % c->n_cstreams]))) return rc;
+        if ((rc = encode_chunk(c, g0, std::min(cg, n_gops - g0), gop_len, qdc, qac, c->cstream[i % c->n_cstreams],
+                               i > 0 && c->skew ? chunk_event(c, 200 + i - 1) : nullptr, c->skew ? chunk_event(c, 200 + i) : nullptr, c->skew))) return rc;
     if ((rc = join_streams(c))) return rc;
     CU(cudaGetLastError());
     return ICSP_OK;

@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <malloc.h>
 #include <vector>
 
 static void die(const char* what, icsp_ctx* ctx)
@@ -44,20 +45,33 @@ static int* zigzag_copy(const int16_t* src)
 
 void single_thread_encoding(FrameData* frames, YCbCr_t* YCbCr, int intra_period, int QstepDC, int QstepAC)
 {
+    // makebitstream ORs the bits of the last, partial byte into a malloc'd (never cleared) buffer (ENC:4875, 4895):
+    // the stock binary gets that buffer from a fresh, zero-filled mmap, which is what the golden files contain.  The CUDA runtime
+    // leaves a well-used heap behind, so pin glibc's mmap threshold: every large allocation of the writer is a fresh mapping again.
+    mallopt(M_MMAP_THRESHOLD, 64 * 1024);
     const int n = YCbCr->nframe, w = YCbCr->width, h = YCbCr->height;
     const int nmb = (w / 16) * (h / 16), ysz = w * h, csz = ysz / 4, fb = ysz + 2 * csz;
     const bool all_intra = intra_period == ALL_INTRA;
     const int gop = all_intra ? 1 : intra_period, full = n / gop, tail = n - full * gop;
 
-    // frames[i].Y / Cb / Cr are already planar (splitFrames, ENC:284-310): three memcpys per frame into pinned memory
+    // input frames into pinned memory.  frames[i].Y is the planar luma (splitFrames, ENC:284-310); frames[i].Cb / Cr were
+    // FREED at the end of splitBlocks (ENC:436-441) — the chroma pixels only survive in the per-block copies
+    // Cbblocks[mb].originalblck8 (ENC:408-424), so the planes are reassembled from those
     uint8_t* i420 = (uint8_t*)icsp_host_alloc_upload((size_t)n * fb);
     uint8_t* recon = (uint8_t*)icsp_host_alloc((size_t)n * fb);
     int16_t* levels = (int16_t*)icsp_host_alloc((size_t)n * nmb * 384 * sizeof(int16_t));
     if (!i420 || !recon || !levels) die("pinned allocation failed", NULL);
+    const int cw = w / 2, cbw = cw / 8;
     for (int i = 0; i < n; i++) {
-        memcpy(i420 + (size_t)i * fb, frames[i].Y, ysz);
-        memcpy(i420 + (size_t)i * fb + ysz, frames[i].Cb, csz);
-        memcpy(i420 + (size_t)i * fb + ysz + csz, frames[i].Cr, csz);
+        uint8_t* dst = i420 + (size_t)i * fb;
+        memcpy(dst, frames[i].Y, ysz);
+        for (int mb = 0; mb < nmb; mb++) {
+            const int x0 = (mb % cbw) * 8, y0 = (mb / cbw) * 8;
+            for (int y = 0; y < 8; y++) {
+                memcpy(dst + ysz + (size_t)(y0 + y) * cw + x0, frames[i].Cbblocks[mb].originalblck8->block[y], 8);
+                memcpy(dst + ysz + csz + (size_t)(y0 + y) * cw + x0, frames[i].Crblocks[mb].originalblck8->block[y], 8);
+            }
+        }
     }
     std::vector<int16_t> mvd((size_t)n * nmb * 2);
     std::vector<uint8_t> acflag((size_t)n * nmb * 6), mpm((size_t)n * nmb * 4), ipm((size_t)n * nmb * 4);
