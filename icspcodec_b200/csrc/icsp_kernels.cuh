@@ -684,6 +684,33 @@ __device__ __forceinline__ uint4 window_chunk(const uint8_t* __restrict__ plane,
     return o;
 }
 
+#ifndef ICSP_ME_RAWCHUNK
+#define ICSP_ME_RAWCHUNK 0   // 1: load the apron byte raw and replicate it at store time (measured 2 % slower: more live registers across the search)
+#endif
+// The same fetch split in two, for the software-pipelined kernel: window_chunk_raw only LOADS (apron chunks: the one edge
+// byte, untouched, in .x), window_chunk_finish turns that into the replicated chunk when the data is consumed a whole
+// macroblock search later.  (Multiplying the byte right after the load made every staging warp wait for the global
+// latency at the top of each macroblock row: 6 % of the kernel's stall samples.)
+__device__ __forceinline__ uint4 window_chunk_raw(const uint8_t* __restrict__ plane, int w, int h, int py, int pxc)
+{
+    const int PH = h + 32;
+    if (py == PH - 1) return make_uint4(0, 0, 0, 0);
+    const int yy = min(max(py - 16, 0), h - 1);
+    const uint8_t* row = plane + (unsigned)(yy * w);
+    const int x0 = pxc * 16 - 16;
+    if (x0 >= 0 && x0 + 16 <= w) return __ldg((const uint4*)(row + (unsigned)x0));
+    return make_uint4((uint32_t)__ldg(row + (x0 < 0 ? 0 : w - 1)), 0, 0, 0);
+}
+__device__ __forceinline__ uint4 window_chunk_finish(uint4 v, int w, int h, int py, int pxc)
+{
+    const int x0 = pxc * 16 - 16;
+    if (py == h + 31 || (x0 >= 0 && x0 + 16 <= w)) return v;
+    const uint32_t r = v.x * 0x01010101u;
+    uint4 o = make_uint4(r, r, r, r);
+    if (x0 >= 0 && pxc * 16 + 16 == w + 32) o.w &= 0x00ffffffu;  // last padded column stays 0
+    return o;
+}
+
 // Stage the window and the current rows of segment (mby, m0..m0+nmbs).  One warp per window row, one lane per
 // 16-byte chunk: copy 0 is the plain window; copy s (s = 1..3) holds the window shifted left by s bytes and stored
 // one word to the right (word i+1 of copy s = window bytes [4i+s, 4i+s+4)), so all four stores are aligned STS.128.
@@ -921,13 +948,21 @@ __device__ __forceinline__ uint4 me_task_load(const Geom& g, const uint8_t* __re
                                               int band, int cur_mby, int m0, int nmbs, int lane)
 {
     uint4 v = make_uint4(0, 0, 0, 0);
+#if ICSP_ME_RAWCHUNK
+    if (task < 16) { if (lane < nmbs + 2) v = window_chunk_raw(refy, g.w, g.h, band * 16 + task, m0 + lane); }
+#else
     if (task < 16) { if (lane < nmbs + 2) v = window_chunk(refy, g.w, g.h, band * 16 + task, m0 + lane); }
+#endif
     else if (task < 32) { if (lane < nmbs) v = __ldg((const uint4*)(cury + (unsigned)((cur_mby * 16 + task - 16) * g.w + (m0 + lane) * 16))); }
     return v;
 }
-__device__ __forceinline__ void me_task_store(const MeLayout& L, uint32_t* s_win, uint8_t* s_cur, int task, int band, uint4 v, int nmbs, int lane)
+__device__ __forceinline__ void me_task_store(const Geom& g, const MeLayout& L, uint32_t* s_win, uint8_t* s_cur, int task, int band, uint4 v, int m0, int nmbs, int lane)
 {
+#if ICSP_ME_RAWCHUNK
+    if (task < 16) me_store_chunk(L, s_win, band * 16 + task, window_chunk_finish(v, g.w, g.h, band * 16 + task, m0 + lane), lane, nmbs + 2);
+#else
     if (task < 16) me_store_chunk(L, s_win, band * 16 + task, v, lane, nmbs + 2);
+#endif
     else if (task < 32) { if (lane < nmbs) *(uint4*)(s_cur + ((task - 16) * L.seg_mbs + lane) * 16) = v; }
 }
 
@@ -939,12 +974,13 @@ __device__ __forceinline__ void me_task_store(const MeLayout& L, uint32_t* s_win
 // already owns.  The three fallback kernels then never have to be launched: as separate launches of 704-thread, 142 KB CTAs
 // they could only be scheduled once a whole SM had drained, and cost each chunk 0.3-0.5 ms of dead time per step although
 // they exit at once on natural content (profiles/README.md, round 2).
-template <int CPITCH, int CSEG>
-__global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L, FramePtrs p, Step st, int fused)
+template <int CPITCH, int CSEG, bool FUSED>
+__global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
 {
     extern __shared__ __align__(16) unsigned char s_me[];
-    __shared__ unsigned s_breaks;
-    if (threadIdx.x == 0) s_breaks = 0;
+    constexpr bool fused = FUSED;
+    unsigned* const s_breaks_p = (unsigned*)(s_me + me_frame_smem_bytes(L));   // FUSED: 16 more bytes of dynamic shared memory
+    if (FUSED && threadIdx.x == 0) *s_breaks_p = 0;
     const int pitch_w = CPITCH ? CPITCH : L.pitch_w, seg_mbs = CSEG ? CSEG : L.seg_mbs;
     const int gop = blockIdx.y, seg = blockIdx.x;
     const int m0 = seg * seg_mbs, nmbs = min(seg_mbs, g.mbw - m0);
@@ -960,7 +996,7 @@ __global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L
     // prologue: bands 0..2 and current rows of macroblock row 0
     for (int band = 0; band < 3; band++)
         for (int task = warp; task < (band == 0 ? 32 : 16); task += nwarps)
-            me_task_store(L, s_win, s_cur0, task, band, me_task_load(g, refy, cury, task, band, 0, m0, nmbs, lane), nmbs, lane);
+            me_task_store(g, L, s_win, s_cur0, task, band, me_task_load(g, refy, cury, task, band, 0, m0, nmbs, lane), m0, nmbs, lane);
     __syncthreads();
 
     const int mbl = warp;   // nwarps == seg_mbs >= nmbs
@@ -1017,20 +1053,20 @@ __global__ void __launch_bounds__(704, 1) me_sad_frame_kernel(Geom g, MeLayout L
                 *(int*)(p.mv + (f * g.nmb + mb) * 2) = ((-wdx) & 0xffff) | ((-wdy) << 16);
                 p.minsad[f * g.nmb + mb] = (int32_t)best;
                 p.memoves[(size_t)gop * g.nmb + mb] = (uint8_t)moves;
-                if (moves < 64) { if (fused) atomicAdd(&s_breaks, 1u); else atomicAdd(&p.meflag[gop], 1u); }
+                if (moves < 64) { if (fused) atomicAdd(s_breaks_p, 1u); else atomicAdd(&p.meflag[gop], 1u); }
             }
         }
         // (3) hand the prefetched rows over; narrow segments (fewer than 16 warps) fetch the rest without overlap
         if (more) {
-            me_task_store(L, s_win, s_cur_next, warp, mby + 3, pre0, nmbs, lane);
-            me_task_store(L, s_win, s_cur_next, warp + nwarps, mby + 3, pre1, nmbs, lane);
+            me_task_store(g, L, s_win, s_cur_next, warp, mby + 3, pre0, m0, nmbs, lane);
+            me_task_store(g, L, s_win, s_cur_next, warp + nwarps, mby + 3, pre1, m0, nmbs, lane);
             for (int task = warp + 2 * nwarps; task < 32; task += nwarps)
-                me_task_store(L, s_win, s_cur_next, task, mby + 3, me_task_load(g, refy, cury, task, mby + 3, mby + 1, m0, nmbs, lane), nmbs, lane);
+                me_task_store(g, L, s_win, s_cur_next, task, mby + 3, me_task_load(g, refy, cury, task, mby + 3, mby + 1, m0, nmbs, lane), m0, nmbs, lane);
         }
         __syncthreads();
     }
     if (!fused) return;
-    const unsigned breaks = s_breaks;           // the loop's last __syncthreads() ordered every increment before this read
+    const unsigned breaks = *s_breaks_p;        // the loop's last __syncthreads() ordered every increment before this read
     if (threadIdx.x == 0) p.meflag[gop] = breaks;
     if (breaks == 0) return;                    // natural content: the speculative state-0 search is the answer
     me_zero_rows(g, L, p, st, gop, seg, s_me);  // which visits have SAD 0, for all 8 start states

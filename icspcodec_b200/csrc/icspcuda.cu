@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -87,6 +89,11 @@ struct icsp_ctx {
     std::vector<cudaEvent_t> free_events;
     cudaEvent_t slots[8] = {};
     char err[256] = "";
+    bool async_err = false;
+    // CUDA graphs of the per-chunk kernel sequences, keyed by everything that shapes them (see run_captured)
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; uint64_t count[32] = {}; };
+    std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
+    bool use_graphs = true;                   // ICSP_GRAPHS=0: plain stream launches                   // a CUDA call inside launch bookkeeping failed (event creation, stream join)
     size_t me_smem = 0, me_frame_smem = 0, intra_smem = 0, chain_smem = 0;
     bool me_persistent = true;
     bool me_fused = true;                     // ICSP_ME_FUSED=0: exact carried-state fallback as three separate launches (A/B)
@@ -211,7 +218,7 @@ cudaEvent_t get_event(icsp_ctx* c)
 {
     if (!c->free_events.empty()) { cudaEvent_t e = c->free_events.back(); c->free_events.pop_back(); return e; }
     cudaEvent_t e = nullptr;
-    cudaEventCreate(&e);
+    if (cudaEventCreate(&e) != cudaSuccess) { c->async_err = true; return nullptr; }   // reported by the next icsp_sync
     return e;
 }
 void fold_pending(icsp_ctx* c)
@@ -242,12 +249,12 @@ struct LaunchScope {
         c->launches++; c->count[k]++;
         if (c->profiling) {
             a = get_event(c); b = get_event(c);
-            cudaEventRecord(a, s);
+            if (a && b) cudaEventRecord(a, s);
         }
     }
     ~LaunchScope()
     {
-        if (c->profiling) { cudaEventRecord(b, s); c->pending.push_back({k, a, b, s}); }
+        if (c->profiling && a && b) { cudaEventRecord(b, s); c->pending.push_back({k, a, b, s}); }
     }
 };
 
@@ -260,6 +267,45 @@ Step make_step(int gop_len, int t, int qdc, int qac)
     st.qmode_ac = qac <= 128 ? 0 : 1;                 // div_m19 is exact while 4080*qac < 2^19
     st.m19_ac = (1 << 19) / qac + 1;
     return st;
+}
+
+// The kernels of one chunk (every step of its GOPs, the fork / join to the high-priority companion stream included) are
+// captured ONCE per shape into a CUDA graph and replayed afterwards: a chunk is 60-130 launches and event operations, i.e.
+// ~0.5 ms of host time, which is what a small batch (one 300-frame stream = 30 GOPs per launch) spends most of its time on.
+// key = (kind, first GOP / stream, count, gop_len, qp_dc, qp_ac, extra): device pointers follow from the first GOP, so
+// equal keys mean equal kernel arguments.  Not used while per-launch profiling events, the DCT tap or experiments are on.
+template <typename F>
+int run_captured(icsp_ctx* c, std::tuple<int, int, int, int, int, int, int> key, cudaStream_t s, F&& enqueue)
+{
+    if (!c->use_graphs || c->profiling || c->d_dct_tap || c->skew) return enqueue();
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        const uint64_t l0 = c->launches;
+        uint64_t c0[K_COUNT];
+        for (int k = 0; k < K_COUNT; k++) c0[k] = c->count[k];
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue();
+        const cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (rc != ICSP_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc != ICSP_OK ? rc : fail(c, ICSP_ERR_CUDA, "CUDA graph capture failed: %s", cudaGetErrorString(e));
+        }
+        icsp_ctx::GraphEntry ent;
+        const cudaError_t ei = cudaGraphInstantiate(&ent.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail(c, ICSP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+        ent.launches = c->launches - l0;
+        for (int k = 0; k < K_COUNT; k++) ent.count[k] = c->count[k] - c0[k];
+        c->launches = l0;                                     // counted again below, like every replay
+        for (int k = 0; k < K_COUNT; k++) c->count[k] = c0[k];
+        it = c->graphs.emplace(key, ent).first;
+    }
+    CU(cudaGraphLaunch(it->second.exec, s));
+    c->launches += it->second.launches;
+    for (int k = 0; k < K_COUNT; k++) c->count[k] += it->second.count[k];
+    return ICSP_OK;
 }
 
 // pointers of the chunk that starts at GOP g0 (frame g0*gop_len): kernels index GOPs from 0 inside a chunk
@@ -317,8 +363,8 @@ cudaStream_t hi_begin(icsp_ctx* c, cudaStream_t s, int& idx)
 void hi_end(icsp_ctx* c, cudaStream_t s, int idx)
 {
     if (idx < 0) return;
-    cudaEventRecord(c->ev_hi[idx][1], c->hstream[idx]);
-    cudaStreamWaitEvent(s, c->ev_hi[idx][1], 0);
+    // a failed join would let the chunk's stream run ahead of the companion kernel: remember it, icsp_sync reports it
+    if (cudaEventRecord(c->ev_hi[idx][1], c->hstream[idx]) != cudaSuccess || cudaStreamWaitEvent(s, c->ev_hi[idx][1], 0) != cudaSuccess) c->async_err = true;
 }
 
 template <bool INTRA, bool QFAST>
@@ -350,9 +396,11 @@ int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream
     }
     {
         LaunchScope ls(c, K_ME_SAD, s);
-        if (c->me_persistent && L.pitch_w == 104 && L.seg_mbs == 22)   // CIF: compile-time pitch / segment width
-            me_sad_frame_kernel<104, 22><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st, fused ? 1 : 0);
-        else if (c->me_persistent) me_sad_frame_kernel<0, 0><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st, fused ? 1 : 0);
+        const bool cif = L.pitch_w == 104 && L.seg_mbs == 22;          // CIF: compile-time pitch / segment width
+        if (c->me_persistent && fused && cif) me_sad_frame_kernel<104, 22, true><<<dim3(L.nseg, G), threads, c->me_frame_smem + 16, s>>>(g, L, p, st);
+        else if (c->me_persistent && fused) me_sad_frame_kernel<0, 0, true><<<dim3(L.nseg, G), threads, c->me_frame_smem + 16, s>>>(g, L, p, st);
+        else if (c->me_persistent && cif) me_sad_frame_kernel<104, 22, false><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
+        else if (c->me_persistent) me_sad_frame_kernel<0, 0, false><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
         else me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0, 1);
     }
     if (fused) return ICSP_OK;
@@ -413,8 +461,13 @@ int encode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, 
 // latency-bound kernels (intra wavefront, DC chains) at the same time, then all in ME, ... and nothing overlaps.  `wait`
 // (recorded by the previous chunk once it is `skew` stages into its pipeline) holds this chunk back at its start, so that
 // the chunks stay out of phase: one chunk's latency-bound kernels then run underneath another's throughput kernels.
+int encode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s, cudaEvent_t wait, cudaEvent_t signal, int skew);
 int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s, cudaEvent_t wait = nullptr, cudaEvent_t signal = nullptr,
                  int skew = 0)
+{
+    return run_captured(c, std::make_tuple(0, g0, G, gop_len, qdc, qac, 0), s, [&] { return encode_chunk_plain(c, g0, G, gop_len, qdc, qac, s, wait, signal, skew); });
+}
+int encode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s, cudaEvent_t wait, cudaEvent_t signal, int skew)
 {
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
     if (wait) CU(cudaStreamWaitEvent(s, wait, 0));
@@ -429,7 +482,12 @@ int encode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
     return ICSP_OK;
 }
 
+int decode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s);
 int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+{
+    return run_captured(c, std::make_tuple(3, g0, G, gop_len, qdc, qac, 0), s, [&] { return decode_chunk_plain(c, g0, G, gop_len, qdc, qac, s); });
+}
+int decode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
 {
     const Geom& g = c->g;
     const FramePtrs p = frame_ptrs(c, g0, gop_len);
@@ -499,18 +557,20 @@ int entropy_chunk(icsp_ctx* c, int ci, int s0, int ns, int gops_per_stream, int 
     e.blkbits = c->d_blkbits + f0 * nmb * 6; e.framebits = c->d_framebits + f0; e.streambits = c->d_streambits + s0;
     e.streamoff = c->d_streamoff + s0; e.total = c->d_chunktotal + ci; e.overflow = c->d_overflow + ci;
     e.bits = c->d_bits + ch.region_off; e.cap_bytes = ch.region_cap;
-    CU(cudaMemsetAsync(e.overflow, 0, sizeof(uint32_t), s));
-    dim3 grid((g.nmb * 6 + EN_THREADS - 1) / EN_THREADS, (unsigned)nf);
-    { LaunchScope ls(c, K_EN_SIZE, s); entropy_size_kernel<<<grid, EN_THREADS, 0, s>>>(g, p, e, gop_len); }
-    { LaunchScope ls(c, K_EN_FSCAN, s); entropy_frame_scan_kernel<<<(unsigned)nf, 256, 0, s>>>(g, e); }
-    {
-        LaunchScope ls(c, K_EN_SSCAN, s);
-        entropy_stream_scan_kernel<<<ns, 32, 0, s>>>(e, fps);
-        entropy_stream_offsets_kernel<<<1, 32, 0, s>>>(e, ns);
-    }
-    { LaunchScope ls(c, K_EN_ZERO, s); entropy_zero_kernel<<<296, 256, 0, s>>>(e); }
-    { LaunchScope ls(c, K_EN_PACK, s); entropy_pack_kernel<<<grid, EN_THREADS, 0, s>>>(g, p, e, gop_len, fps); }
-    return ICSP_OK;
+    return run_captured(c, std::make_tuple(2, s0, ns, gop_len, gops_per_stream, ci, 0), s, [&]() -> int {
+        CU(cudaMemsetAsync(e.overflow, 0, sizeof(uint32_t), s));
+        dim3 grid((g.nmb * 6 + EN_THREADS - 1) / EN_THREADS, (unsigned)nf);
+        { LaunchScope ls(c, K_EN_SIZE, s); entropy_size_kernel<<<grid, EN_THREADS, 0, s>>>(g, p, e, gop_len); }
+        { LaunchScope ls(c, K_EN_FSCAN, s); entropy_frame_scan_kernel<<<(unsigned)nf, 256, 0, s>>>(g, e); }
+        {
+            LaunchScope ls(c, K_EN_SSCAN, s);
+            entropy_stream_scan_kernel<<<ns, 32, 0, s>>>(e, fps);
+            entropy_stream_offsets_kernel<<<1, 32, 0, s>>>(e, ns);
+        }
+        { LaunchScope ls(c, K_EN_ZERO, s); entropy_zero_kernel<<<296, 256, 0, s>>>(e); }
+        { LaunchScope ls(c, K_EN_PACK, s); entropy_pack_kernel<<<grid, EN_THREADS, 0, s>>>(g, p, e, gop_len, fps); }
+        return ICSP_OK;
+    });
 }
 
 // GOPs per chunk: enough chunks to overlap (>= 2 per compute stream) but each big enough to fill the GPU
@@ -623,6 +683,7 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     if (const char* e = getenv("ICSP_ME_FUSED")) c->me_fused = atoi(e) != 0;
     if (const char* e = getenv("ICSP_TR_V1")) c->tr_v1 = atoi(e) != 0;
     if (const char* e = getenv("ICSP_SKEW")) c->skew = std::max(0, atoi(e));
+    if (const char* e = getenv("ICSP_GRAPHS")) c->use_graphs = atoi(e) != 0;
     c->intra_smem = intra_smem_bytes(g);
     c->chain_smem = (size_t)(6 * g.nmb + 3) * 8 + 32;  // staged: one 8-byte slot per block + a sentinel per plane
     if (c->chain_smem > 100 * 1024) { c->chain_staged = 0; c->chain_smem = (size_t)6 * g.nmb * sizeof(int) + 32; }
@@ -644,9 +705,11 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
         }
         CUB(cudaFuncSetAttribute(me_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         CUB(cudaFuncSetAttribute(me_zero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));     // it also has a few static bytes
-        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<104, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-        if ((size_t)optin - 1024 < c->me_frame_smem) c->me_persistent = false;
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<104, 22, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(me_sad_frame_kernel<104, 22, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        if ((size_t)optin < c->me_frame_smem + 16) c->me_persistent = false;
         CUB(cudaFuncSetAttribute(intra_luma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
         CUB(cudaFuncSetAttribute(intra_luma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
         CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -666,6 +729,7 @@ void icsp_destroy(icsp_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (auto& e : c->ev_join) if (e) cudaEventDestroy(e);
@@ -706,6 +770,7 @@ int icsp_sync(icsp_ctx* c)
     if (!c) return ICSP_ERR_PARAM;
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->async_err) { c->async_err = false; return fail(c, ICSP_ERR_CUDA, "a CUDA event / stream-join call failed while launching: %s", cudaGetErrorString(cudaGetLastError())); }
     return ICSP_OK;
 }
 

@@ -30,6 +30,17 @@
 #include "bitstream.h"
 
 namespace {
+// ICSPENC_TIMING=1: where the wall time of a run goes (stderr)
+struct PhaseClock {
+    const bool on = getenv("ICSPENC_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what)
+    {
+        const auto n = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[icspenc timing] %-34s %8.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
 struct Options {
     std::string input;
     int frames = 1;             // README.md:30 documents 1 (the reference leaves it uninitialised, ENC:84-91)
@@ -148,8 +159,10 @@ int run_batch(const Options& o)
         if (mine <= 0) return;
         const int W = std::max(1, std::min(o.wave, mine));
         auto bail = [&](const std::string& m) { errs[d] = m; failed++; };
+        PhaseClock pc;
         icsp_ctx* ctx = nullptr;
         if (icsp_create(&ctx, d, o.width, o.height, W * std::max(full * gop, tail))) return bail(icsp_last_error(nullptr));
+        pc.lap("batch: CUDA init + icsp_create");
         // double buffers: frames in (write-combined pinned), reconstruction and bits out (pinned)
         struct Buf { uint8_t *in = nullptr, *tail_in = nullptr, *rec = nullptr, *bits = nullptr; size_t bits_cap = 0;
                      std::vector<uint64_t> nbits, off, tnbits, toff, rows, trows; uint8_t* tbits = nullptr; size_t tbits_cap = 0; int count = 0, first = 0; } buf[2];
@@ -248,7 +261,9 @@ int run_batch(const Options& o)
         // pipeline over waves: load(i+1) | encode(i) | store(i-1)
         const int nwaves = (mine + W - 1) / W;
         std::future<void> loading, storing;
+        pc.lap("batch: pinned buffers");
         load(buf[0], s_begin, std::min(W, mine));
+        pc.lap("batch: first wave read");
         for (int wv = 0; wv < nwaves && !failed; wv++) {
             Buf& cur = buf[wv & 1];
             Buf& nxt = buf[(wv + 1) & 1];
@@ -263,7 +278,9 @@ int run_batch(const Options& o)
             if (!rc) storing = std::async(std::launch::async, [&] { store(cur); });
         }
         if (loading.valid()) loading.get();
+        pc.lap("batch: waves (encode | read | write)");
         if (storing.valid()) storing.get();
+        pc.lap("batch: last wave write");
         for (auto& b : buf) { icsp_host_free(b.in); icsp_host_free(b.tail_in); icsp_host_free(b.rec); icsp_host_free(b.bits); icsp_host_free(b.tbits); }
         icsp_destroy(ctx);
     };
@@ -308,12 +325,15 @@ int main(int argc, char** argv)
     const size_t fb = (size_t)o.width * o.height * 3 / 2;
     const int n = o.frames;
 
+    PhaseClock pc;
     FILE* fi = fopen(o.input.c_str(), "rb");
     if (!fi) { fprintf(stderr, "[ERROR] cannot open %s\n", o.input.c_str()); return 1; }
     uint8_t* frames = (uint8_t*)icsp_host_alloc_upload((size_t)n * fb);   // the CPU only writes it (fread), the GPUs read it
+    pc.lap("CUDA init + pinned input buffer");
     if (!frames) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host, %zu bytes); is a CUDA device present? libicspcuda has no CPU fallback\n", (size_t)n * fb); return 1; }
     if (fread(frames, fb, n, fi) != (size_t)n) { fprintf(stderr, "[ERROR] %s holds fewer than %d frames of %dx%d\n", o.input.c_str(), n, o.width, o.height); return 1; }
     fclose(fi);
+    pc.lap("read input file");
 
     // SoA outputs (pinned)
     const size_t N = (size_t)n * nmb;
@@ -330,6 +350,7 @@ int main(int argc, char** argv)
     uint8_t* recon = o.recon ? (uint8_t*)icsp_host_alloc((size_t)n * fb) : nullptr;
     if (o.recon && !recon) { fprintf(stderr, "[ERROR] fail memory allocation (pinned host)\n"); return 1; }
 
+    pc.lap("pinned output buffers");
     const auto t0 = std::chrono::steady_clock::now();
     // frame loop: I-frame iff n % intraPeriod == 0 (0 = all intra).  Closed GOPs are independent jobs
     // (ICSP_thread.cpp:39-77): full GOPs are sharded contiguously over the GPUs, the tail GOP goes to the last one.
@@ -409,6 +430,7 @@ int main(int argc, char** argv)
     for (auto& s : shards)
         if (s.rc) { fprintf(stderr, "[ERROR] GPU %d: %s (code %d)\n", s.device, s.err.c_str(), s.rc); return 1; }
     const auto t1 = std::chrono::steady_clock::now();
+    pc.lap("contexts + device calls");
     if (!o.quiet)
         for (int f = 0; f < n; f++) printf("Encoding FRAME_%03d(%c) done!\n", f, (o.ip == 0 || f % o.ip == 0) ? 'I' : 'P');
 
@@ -462,6 +484,7 @@ int main(int argc, char** argv)
         fwrite(recon, fb, n, fr);
         fclose(fr);
     }
+    pc.lap("bit concatenation + file writes");
     if (o.psnr) {   // mean over frames of 20*log10(255/sqrt(MSE_Y)), the reference decoder's figure (DEC.h:332-348)
         double acc = 0;
         for (auto& s : shards)

@@ -2,10 +2,11 @@
  * checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.  The product
  * (libicspcuda / icspenc / icspdec) never links, loads or calls anything in this directory.
  *
- * Parity status: PINNED — oracle/check_oracle.py runs the unmodified compiled reference
- * (oracle/_ref, built from /root/reference by oracle/build_ref.sh) on seeded synthetic clips and
- * requires byte-identical .bin, test_yuv.yuv, decoder YUV, full MVs and DCT/IDCT doubles
- * (see tests/test_oracle_vs_ref.py and tests/golden/).
+ * Parity status: PINNED — tests/golden/make_golden.py and make_golden_full.py run the unmodified compiled
+ * reference (oracle/_ref, built from /root/reference by oracle/build_ref.sh) on seeded synthetic clips (12-frame
+ * cases and the 300-frame BASELINE.json configs) and store its outputs; tests/test_oracle.py requires this port to
+ * reproduce them byte for byte: .bin, test_yuv.yuv, decoder YUV, full MVs, DCT/IDCT doubles (0 ulp), and — when
+ * oracle/_ref is present — compares against the reference binaries run live (test_oracle_vs_live_reference).
  *
  * SoA layout shared with include/icspcuda.h (nmb = (w/16)*(h/16), fb = w*h*3/2):
  *   levels  int16 [nframes][nmb][6][64]  zig-zag order, blocks Y0..Y3,Cb,Cr, DC already DPCM'd

@@ -472,3 +472,33 @@ def test_dct_tap_in_pipeline(gpu, oracle):
     assert np.array_equal(res.recon[:2], oracle.encode(clip[:2], W, H, 8, 8, 2).recon)      # the tap changes nothing else
     rp = gpu.inter_frame(clip[1:2], res.recon[0:1], 8, 8, with_dct=True)
     assert np.array_equal(rp.dct[0], oracle.encode(clip[:2], W, H, 8, 8, 2, with_dct=True).dct[1])
+
+
+def test_cuda_graph_replay_matches_plain_launches(oracle, monkeypatch):
+    """The per-chunk kernel sequences are captured into CUDA graphs on first use and replayed afterwards: first call (capture +
+    launch), replays, a different shape in between, and a context with ICSP_GRAPHS=0 must all give the oracle's bits."""
+    from icspcodec_b200 import IcspCuda
+    clips = [synth.make_clip("highmotion", 6, 40 + i) for i in range(3)] + [synth.make_clip("flat", 6, 7)]
+    frames = np.concatenate(clips, axis=0)
+    want = [oracle.encode(c, W, H, 8, 8, 3) for c in clips]
+
+    def check(ctx):
+        for rep in range(3):                                   # capture, then two replays
+            res = ctx.encode_gops(frames, 8, 3, 8, 8)
+            for i, s in enumerate(want):
+                sub = type(res)(**{k: (None if getattr(res, k) is None else getattr(res, k)[6 * i:6 * i + 6]) for k in res.__dataclass_fields__})
+                assert_syntax_equal(sub, s, what=f"rep {rep} clip {i}: ")
+            if rep == 0:                                       # another shape in between: its own graph, must not disturb the first
+                other = ctx.encode_gops(frames[:6], 1, 6, 16, 16)
+                assert np.array_equal(other.recon, oracle.encode(clips[0], W, H, 16, 16, 6).recon)
+        bodies, sbits, _ = ctx.encode_streams(frames, 4, 2, 3, 8, 8)
+        bodies2, sbits2, _ = ctx.encode_streams(frames, 4, 2, 3, 8, 8)
+        assert np.array_equal(sbits, sbits2) and all(np.array_equal(a, b) for a, b in zip(bodies, bodies2))
+        return ctx.launch_count()
+
+    with IcspCuda(W, H, max_frames=32) as ctx:
+        with_graphs = check(ctx)
+    monkeypatch.setenv("ICSP_GRAPHS", "0")
+    with IcspCuda(W, H, max_frames=32) as ctx:
+        plain = check(ctx)
+    assert with_graphs == plain                                # replays are counted like the launches they contain

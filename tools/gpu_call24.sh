@@ -1,0 +1,2 @@
+#!/usr/bin/env bash
+timeout 1700 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
