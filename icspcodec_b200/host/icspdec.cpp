@@ -238,7 +238,7 @@ int main(int argc, char** argv)
     std::vector<std::string> pos;
     int gpus = 1;
     std::string outname, idxname, batch;
-    int wave = 16, io_threads = 0;
+    int wave = 8, io_threads = 0;
     bool use_index = true;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -250,6 +250,12 @@ int main(int argc, char** argv)
         else if (a == "--no-index") use_index = false;
         else if (a == "--out" && i + 1 < argc) outname = argv[++i];
         else pos.push_back(a);
+    }
+    // CUDA initialises every visible device (≈0.7 s each on a multi-GPU box): expose only the ones this run uses
+    if (!getenv("CUDA_VISIBLE_DEVICES") && gpus >= 1 && gpus <= 16) {
+        std::string vis;
+        for (int d = 0; d < gpus; d++) vis += (d ? "," : "") + std::to_string(d);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
     }
     if (!batch.empty()) {
         if (pos.empty()) { fprintf(stderr, "usage: icspdec --batch <list.txt> <nframes> [--gpus G] [--wave S] [--io-threads T] [--no-index]\n"); return 1; }
