@@ -52,6 +52,7 @@ struct Options {
     bool host_entropy = false;  // --host-entropy: download the syntax arrays and entropy-code on the CPU (round-1 path)
     std::string batch;          // --batch <list>: many streams, one process
     int wave = 8, io_threads = 0;
+    bool plan = false;          // --plan: print the GPU shard plan (one line per shard) and exit; touches no device
 };
 
 void help()
@@ -63,6 +64,7 @@ void help()
            "--qpdc : QP of DC\n--qpac : QP of AC\n--intraPeriod: period of intra frame(0: All intra)\n"
            "--EnMultiThread: host threads for the entropy coder (0 = all cores)\n"
            "--gpus: GPUs to shard the GOPs over (default 1)\n--no-recon: do not write test_yuv.yuv\n"
+           "--plan: print the shard plan for --gpus (GOP ranges, or stream ranges with --batch) and exit\n"
            "--batch <list>: encode every stream listed in <list> (one path per line) in one process, sharded over the GPUs;\n"
            "                --wave S streams per device call (default 8), --io-threads T file threads per GPU\n"
            "--host-entropy: entropy-code on the CPU instead of the GPU\n--psnr: print the average luma PSNR (computed on the GPU; works with --no-recon)\n--help : help message\n");
@@ -94,6 +96,7 @@ int parse(int argc, char** argv, Options& o)
         else if (a == "--host-entropy") o.host_entropy = true;
         else if (a == "--psnr") o.psnr = true;
         else if (a == "--index") o.index = true;
+        else if (a == "--plan") o.plan = true;
         else if (a == "--quiet") o.quiet = true;
         else if (a[0] == '-') { fprintf(stderr, "[ERROR] uncorrect parameters in parsing_command\n"); return -1; }
     }
@@ -109,6 +112,26 @@ struct Shard {          // one GPU's contiguous range of GOPs
     std::vector<uint64_t> sse;  // --psnr: [frames][3]
     std::vector<std::vector<uint64_t>> rows;   // --index: per segment, [frames][mbh] bit offsets inside the segment
 };
+
+// The two sharding rules of SURVEY §8e (mirrored for the Python side by icspcodec_b200/sharding.py; tests/test_multi_rank_cpu.py
+// holds the two to the same plan through --plan).  Closed GOPs are independent jobs (ICSP_thread.cpp:39-77): full GOPs are split
+// contiguously over the GPUs, the tail GOP (n % intraPeriod frames) goes to the last one.
+std::vector<Shard> gop_shards(int n, int ip, int gpus)
+{
+    const int gop = ip == 0 ? 1 : ip, full = n / gop, tail = n - full * gop, G = std::max(1, gpus);
+    std::vector<Shard> shards;
+    for (int d = 0; d < G; d++) {
+        const int g0 = (int)((long long)full * d / G), g1 = (int)((long long)full * (d + 1) / G);
+        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, "", {}, {}, {}});
+    }
+    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}, {}, {}});
+    return shards;
+}
+// whole streams per GPU: device d of G takes streams [S*d/G, S*(d+1)/G)
+inline std::pair<int, int> stream_shard(int S, int d, int G)
+{
+    return {(int)((long long)S * d / G), (int)((long long)S * (d + 1) / G)};
+}
 
 // ---- batch mode: N independent streams, one process ---------------------------------------------------------------------
 // parallel helper: run fn(i) for i in [0, n) on `threads` threads
@@ -147,6 +170,10 @@ int run_batch(const Options& o)
     const size_t fb = (size_t)o.width * o.height * 3 / 2;
     const int gop = o.ip == 0 ? 1 : o.ip, full = n / gop, tail = n - full * gop;
     const int G = std::max(1, std::min(o.gpus, S));
+    if (o.plan) {
+        for (int d = 0; d < G; d++) printf("streams device=%d begin=%d end=%d\n", d, stream_shard(S, d, G).first, stream_shard(S, d, G).second);
+        return 0;
+    }
     const int hw = std::max(1, (int)std::thread::hardware_concurrency());
     const int io = o.io_threads > 0 ? o.io_threads : std::max(2, hw / G);
     std::atomic<int> failed{0};
@@ -155,7 +182,7 @@ int run_batch(const Options& o)
     const auto t0 = std::chrono::steady_clock::now();
 
     auto gpu_thread = [&](int d) {
-        const int s_begin = (int)((long long)S * d / G), s_end = (int)((long long)S * (d + 1) / G);
+        const int s_begin = stream_shard(S, d, G).first, s_end = stream_shard(S, d, G).second;
         const int mine = s_end - s_begin;
         if (mine <= 0) return;
         const int W = std::max(1, std::min(o.wave, mine));
@@ -330,6 +357,11 @@ int main(int argc, char** argv)
         fprintf(stderr, "[ERROR] uncorrect parameters (need -i, -n > 0, QP in 1..255, intraPeriod in 0..63, width/height multiples of 16)\n");
         return 1;
     }
+    if (o.plan) {
+        for (const Shard& s : gop_shards(o.frames, o.ip, o.gpus))
+            printf("gops device=%d first_frame=%d n_gops=%d gop_len=%d\n", s.device, s.first_frame, s.n_gops, s.gop_len);
+        return 0;
+    }
     const size_t us = o.input.find('_');
     if (us == std::string::npos) { fprintf(stderr, "[ERROR] input file name must contain '_' (encoder_main.cpp:13)\n"); return 1; }
     const std::string slash_stripped = o.input.substr(0, us);
@@ -366,15 +398,8 @@ int main(int argc, char** argv)
     const auto t0 = std::chrono::steady_clock::now();
     // frame loop: I-frame iff n % intraPeriod == 0 (0 = all intra).  Closed GOPs are independent jobs
     // (ICSP_thread.cpp:39-77): full GOPs are sharded contiguously over the GPUs, the tail GOP goes to the last one.
-    const int gop = o.ip == 0 ? 1 : o.ip;
-    const int full = n / gop, tail = n - full * gop;
     const int G = std::max(1, o.gpus);
-    std::vector<Shard> shards;
-    for (int d = 0; d < G; d++) {
-        const int g0 = (int)((long long)full * d / G), g1 = (int)((long long)full * (d + 1) / G);
-        if (g1 > g0) shards.push_back({d, g0 * gop, g1 - g0, gop, 0, "", {}, {}, {}});
-    }
-    if (tail) shards.push_back({G - 1, full * gop, 1, tail, 0, "", {}, {}, {}});
+    std::vector<Shard> shards = gop_shards(n, o.ip, G);
     auto run_shard = [&](Shard& s) {
         const int cnt = s.n_gops * s.gop_len;
         int call_frames = 4096;                                    // bound device memory per call

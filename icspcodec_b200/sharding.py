@@ -1,6 +1,7 @@
 """GOP sharding across GPUs: closed GOPs share no state, so a sequence (or a batch of streams) is
 split into contiguous GOP ranges, one per device, with no data-path collective; the host concatenates the per-GOP
-results in order.  Same rule as icspenc.cpp (`--gpus N`)."""
+results in order.  Python mirror of the two rules in host/icspenc.cpp (`gop_shards`, `stream_shard`); used by bench.py's
+strong-scaling leg and the 2-rank gloo test, and held to the CLI's own plan (`icspenc --plan`) by tests/test_multi_rank_cpu.py."""
 from __future__ import annotations
 
 from dataclasses import dataclass

@@ -27,6 +27,33 @@ def test_shard_rules():
     assert [len(r) for r in stream_shards(64, 8)] == [8] * 8 and [len(r) for r in stream_shards(3, 2)] == [1, 2]
 
 
+ICSPENC = os.path.join(os.path.dirname(GOLD), "..", "icspcodec_b200", "host", "icspenc")
+
+
+@pytest.mark.parametrize("n,ip,gpus", [(300, 10, 8), (300, 10, 1), (37, 10, 2), (5, 0, 4), (3, 10, 4), (299, 7, 3), (64, 63, 8)])
+def test_icspenc_plan_is_the_same_gop_rule(n, ip, gpus):
+    """The product CLI (C++) and the Python mirror must shard identically: `icspenc --plan` prints its plan without a device."""
+    import re
+    import subprocess
+    out = subprocess.run([ICSPENC, "-i", "x_cif.yuv", "-n", str(n), "-q", "8", "--intraPeriod", str(ip), "--gpus", str(gpus), "--plan"],
+                         capture_output=True, text=True, check=True).stdout
+    got = [tuple(int(v) for v in re.findall(r"=(\d+)", line)) for line in out.splitlines() if line.startswith("gops ")]
+    assert got == [(x.device, x.first_frame, x.n_gops, x.gop_len) for x in gop_shards(n, ip, gpus)]
+
+
+@pytest.mark.parametrize("streams,gpus", [(64, 8), (3, 2), (5, 4), (2, 8)])
+def test_icspenc_plan_is_the_same_stream_rule(tmp_path, streams, gpus):
+    import re
+    import subprocess
+    lst = tmp_path / "list.txt"
+    lst.write_text("".join(f"s{i}_cif.yuv\n" for i in range(streams)))
+    out = subprocess.run([ICSPENC, "--batch", str(lst), "-n", "30", "-q", "8", "--intraPeriod", "10", "--gpus", str(gpus), "--plan"],
+                         capture_output=True, text=True, check=True).stdout
+    got = [tuple(int(v) for v in re.findall(r"=(\d+)", line)) for line in out.splitlines() if line.startswith("streams ")]
+    g = min(gpus, streams)      # the CLI never opens more devices than it has streams
+    assert got == [(d, r.start, r.stop) for d, r in enumerate(stream_shards(streams, g))]
+
+
 def _worker(rank, world, port, case, out_q):
     import torch
     import torch.distributed as dist
