@@ -196,13 +196,19 @@ __device__ __forceinline__ void mv_predictor(const int16_t* mv, int mbw, int mb,
     else py = y1 > y2 ? y1 : y2;
 }
 
-// `staged` != 0: every block owns one 8-byte shared-memory slot that first holds its input (raw DC as a double when
-// encoding, DC level when decoding) and, once the chain has passed, {reconstructed DC, DC level}; the 115 dependent
-// waves then touch shared memory only (8 bytes per block: 19 KB for CIF, so ~11 frames are resident per SM).  All 128
-// threads stage the inputs in and the results out (coalesced over the macroblock-major global arrays, scattered into the
-// plane-raster slots); only the wave walk itself is one warp per plane.  Large frames fall back to staged == 0 (int map
-// only, inputs/outputs in global memory inside the chain).
-// slot index of block k of macroblock mb: luma plane-raster [bh][bw] at 0 (+1 sentinel), Cb [nmb] (+1), Cr [nmb] (+1)
+// `staged` != 0: every block owns one 4-byte shared-memory slot that first holds its input and, once the chain has passed,
+// {reconstructed DC (low half), DC level (high half)} as two int16 (|raw DC| <= 2040 for 8-bit video, so |rec| <= 2040 + Q and
+// |level| <= 4335 fit); the dependent waves then touch shared memory only (9.5 KB for CIF: 16 frames per SM, the thread limit).
+// Input of a slot when decoding: the DC level.  When encoding: the raw DC is a double and the reference's chain is
+//     L = (int)trunc|floor((raw - P) + 0.5) / Q            (ENC:2780 / ENC:4642 after DPCM_DC_block, P the integer predictor)
+// whose roundings move the value by < 2^-38 while |raw| < 2^13, so with xs = raw + 0.5, m = floor(xs), g = xs - m the result is the INTEGER
+// expression floor: m - P, trunc: m - P (+1 if m - P < 0) whenever g is not within `amb_eps` (2^-30) of 0 or 1 — the slot holds
+// (m << 1) and the dependent path of the chain has no FP64 and no conversion on it.  A block whose g IS that close to an integer
+// (probability ~2^-29; forced for every block by ICSP_DC_EPS=1 in the tests), or whose |raw + 0.5| >= 2^13, carries bit 0 and takes the reference's double
+// sequence from the raw value in global memory.  All 128 threads stage the inputs in (loads batched four deep) and the results
+// out (coalesced over the macroblock-major global arrays, scattered into the plane-raster slots); only the wave walk itself is
+// one warp per plane.  Large frames fall back to staged == 0 (int map only, inputs/outputs in global memory inside the chain).
+// slot index of block k of macroblock mb: luma plane-raster [bh][bw] at 0 (+1 unused), Cb [nmb] (+1), Cr [nmb] (+1)
 __device__ __forceinline__ int chain_slot(const Geom& g, int mb, int k)
 {
     if (k >= 4) return 4 * g.nmb + 1 + (k - 4) * (g.nmb + 1) + mb;
@@ -216,8 +222,64 @@ __device__ __forceinline__ int chain_mbmajor(const Geom& g, int pl, int i)
     const int by = (int)__umulhi((unsigned)i, g.magic_bw), bx = i - by * g.bw;
     return ((by >> 1) * g.mbw + (bx >> 1)) * 6 + (((by & 1) << 1) | (bx & 1));
 }
+// The wave walk of one plane by one warp.  Each lane owns ONE block row and walks it left to right, one block per step, two
+// steps behind the lane above (the UR dependency): at step w lane l codes block (w - 2l) of its row.  Its left neighbour is
+// its own previous result (a register); UR is the latest result of the lane above — one warp shuffle per step — and U / UL
+// are the two values that shuffle returned before.  Rows are taken 32 at a time, then 31: in every pass after the first, lane 0 does
+// not code anything, it REPLAYS the last row of the previous pass from the slots so that lane 1 sees its neighbours the
+// same way as every other lane.  Boundary rules of A.5 without branches: a lane that is not yet inside its row forwards
+// what it receives, so at bx == 0 its "left neighbour" equals U and med3(U, U, c) = U; the top row uses med3(L, L, c) = L
+// with L starting at 1024.  The input of the next block is prefetched one step ahead and results are stored fire-and-forget:
+// the dependent path of a step is shuffle -> select -> median -> subtract -> integer divide -> multiply-add.
+template <bool CHROMA, bool DECODE>
+__device__ __forceinline__ void chain_walk(const Geom& g, int* slot, const double* __restrict__ raw, int pl, int bw, int bh, int lane,
+                                           unsigned magic, int q)
+{
+    const int urm = bw - 1;          // chroma: UR unless bx == bw-1; luma odd rows: UR iff bx is even (bw is even, so bw-1 is odd)
+    for (int first = 0;;) {                                      // row of lane 0: row 0, or the replayed last row of the pass before
+        const int by = first + lane;
+        const bool replay = first > 0 && lane == 0;
+        const int rows = min(32, bh - first);
+        const int bw_l = lane < rows ? bw : 0;                   // lanes without a row are never active
+        const bool top = by == 0;
+        const int m = (!CHROMA && (by & 1)) ? 1 : urm;           // ur = (bx & m) != m
+        const int steps = bw + 2 * (rows - 1);
+        int* sp = slot + by * bw - 2 * lane;                     // sp[w] is the slot of the block coded at step w
+        int bx = -2 * lane;
+        int h1 = 1024, q1 = 0, q2 = 0;
+        int in = bx == 0 && bw_l ? sp[0] : 0;
+#pragma unroll 2
+        for (int w = 0; w < steps; w++, bx++) {
+            const int sent = __shfl_up_sync(0xffffffffu, h1, 1);
+            const bool act = (unsigned)bx < (unsigned)bw_l;
+            const int in_n = (unsigned)(bx + 1) < (unsigned)bw_l ? sp[w + 1] : 0;
+            const int c = (bx & m) != m ? sent : q2;
+            const int b = top ? h1 : q1;
+            const int P = max(min(h1, b), min(max(h1, b), c));   // med3 is a true median (ENC:3677-3679)
+            int L = in;
+            if (!DECODE) {                                       // DPCM_DC_block: D -= P, then quantise
+                int d = (in >> 1) - P;
+                if (!CHROMA) d += (int)((unsigned)d >> 31);      // truncation toward zero of the non-integer (m - P) + g
+                L = div_magic(d, magic);
+                if (in & 1) {                                    // raw DC + 0.5 too close to an integer: the reference's double sequence
+                    if (act && !replay) L = quant_magic(__dsub_rn(raw[chain_mbmajor(g, pl, by * bw + bx)], (double)P), magic, CHROMA);
+                }
+            }
+            int res = L * q + P;                                 // IQuantization + IDPCM_DC_block
+            if (act && !replay) sp[w] = (int)__byte_perm((unsigned)res, (unsigned)L, 0x5410);
+            if (replay) res = (int)(short)in;                    // stored {rec, level}: the sign-extended low half
+            h1 = act ? res : sent;
+            q2 = q1; q1 = sent;
+            in = in_n;
+        }
+        __syncwarp();                                            // the next pass replays this pass's last row from shared memory
+        if (first + rows >= bh) break;
+        first += rows - 1;
+    }
+}
+
 __global__ void __launch_bounds__(128) dc_chain_kernel(const __grid_constant__ Geom g, const __grid_constant__ FramePtrs p,
-                                                        const __grid_constant__ Step st, int decode, int staged)
+                                                        const __grid_constant__ Step st, int decode, int staged, float amb_eps)
 {
     extern __shared__ __align__(16) unsigned char s_chain[];
     const int nblk = 6 * g.nmb;
@@ -232,69 +294,37 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(const __grid_constant__ G
     const int nwaves = (bw - 1) + 2 * (bh - 1) + 1;
     const bool walker = warp < 3 && !(warp == 0 && st.intra);   // intra luma DCs are chained inside the wavefront kernel
     if (staged) {
-        double* slots = (double*)s_chain;
-        int* dc2s = (int*)s_chain;                           // {dc, level} pairs: dc at even ints
-        for (int i6 = threadIdx.x; i6 < nblk; i6 += 128) {
-            const int mb = (int)__umulhi((unsigned)i6, 0x2aaaaaabu), k = i6 - 6 * mb;    // i6 / 6 for i6 < 2^31
-            if (st.intra && k < 4) continue;
-            const int s = chain_slot(g, mb, k);
-            if (decode) dc2s[2 * s + 1] = lvf[i6 * 64];
-            else slots[s] = raw[i6];
+        int* slots = (int*)s_chain;
+        const double eps = (double)amb_eps;
+        for (int i0 = threadIdx.x; i0 < nblk; i0 += 4 * 128) {
+            double rv[4];
+            int lv[4], sl[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i6 = i0 + u * 128;
+                const int mb = (int)__umulhi((unsigned)i6, 0x2aaaaaabu), k = i6 - 6 * mb;    // i6 / 6 for i6 < 2^31
+                sl[u] = (i6 < nblk && !(st.intra && k < 4)) ? chain_slot(g, mb, k) : -1;
+                rv[u] = 0.0; lv[u] = 0;
+                if (sl[u] >= 0) { if (decode) lv[u] = lvf[i6 * 64]; else rv[u] = raw[i6]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (sl[u] < 0) continue;
+                if (decode) { slots[sl[u]] = lv[u]; continue; }
+                const double xs = __dadd_rn(rv[u], 0.5);
+                const int m = __double2int_rd(xs);
+                const double gfr = __dsub_rn(xs, (double)m);                                  // exact
+                const bool amb = !(gfr >= eps && gfr <= 1.0 - eps) || !(fabs(xs) < 8192.0);   // 8-bit video: |raw| <= 2040
+                slots[sl[u]] = (int)((unsigned)m << 1) | (amb ? 1 : 0);
+            }
         }
-        if (threadIdx.x < 3) dc2s[2 * (threadIdx.x == 0 ? 4 * g.nmb : 4 * g.nmb + threadIdx.x * (g.nmb + 1))] = 1024;   // sentinels: predictor of block (0,0)
         __syncthreads();
         if (walker) {
-            // Each lane owns ONE block row (rows are taken 32 at a time) and walks it left to right, one block per step, two
-            // steps behind the lane above (the UR dependency): at step w lane l codes block (w - 2l, r0 + l).  Its left
-            // neighbour is its own previous result (a register); U, UR and UL are the last three results of the lane above,
-            // fetched with three warp shuffles.  Nothing on the dependent path touches shared memory (the raw DC of the next
-            // block is prefetched one step ahead, results are stored fire-and-forget), so a step costs one shuffle + median +
-            // quantiser latency instead of a shared-memory round trip, index arithmetic and a warp barrier.
             const int base = chroma ? 4 * g.nmb + 1 + (warp - 1) * (g.nmb + 1) : 0;
-            double* slot = slots + base;
-            int* dc2 = dc2s + 2 * base;
-            for (int r0 = 0; r0 < bh; r0 += 32) {
-                const int rows = min(32, bh - r0), by = r0 + lane;
-                const bool row_ok = lane < rows;
-                const int steps = (bw - 1) + 2 * (rows - 1) + 1;
-                int h1 = 0, h2 = 0, h3 = 0;                 // my results at bx-1, bx-2, bx-3 (h1 = left neighbour)
-                int bx = -2 * lane;
-                const int rowbase = by * bw;
-                double raw = 0.0;
-                int lvl = 0;
-                if (row_ok && bx == 0) { if (decode) lvl = dc2[2 * rowbase + 1]; else raw = slot[rowbase]; }
-                for (int w = 0; w < steps; w++, bx++) {
-                    // the lane above is one step ahead in x: its h1 is my UR, h2 my U, h3 my UL
-                    int ur_v = __shfl_up_sync(0xffffffffu, h1, 1), u_v = __shfl_up_sync(0xffffffffu, h2, 1), ul_v = __shfl_up_sync(0xffffffffu, h3, 1);
-                    const bool act = row_ok && bx >= 0 && bx < bw;
-                    if (lane == 0 && r0 > 0 && act) {       // first row of a later pass: the row above was stored by the previous pass
-                        const int* up = dc2 + 2 * (rowbase - bw + bx);
-                        u_v = up[0];
-                        ur_v = bx + 1 < bw ? up[2] : 0;
-                        ul_v = bx > 0 ? up[-2] : 0;
-                    }
-                    // prefetch the input of my next block (address known one step ahead)
-                    double raw_n = 0.0;
-                    int lvl_n = 0;
-                    if (row_ok && bx + 1 >= 0 && bx + 1 < bw) { if (decode) lvl_n = dc2[2 * (rowbase + bx + 1) + 1]; else raw_n = slot[rowbase + bx + 1]; }
-                    int res = 0;
-                    if (act) {
-                        // A.5 without divergent branches: the three neighbours whose median is the predictor (single-neighbour cases
-                        // repeat that neighbour); med3 is a true median (ENC:3677-3679)
-                        const bool ur = chroma ? (bx != bw - 1) : ((bx & 1) == 0 || ((by & 1) == 0 && bx != bw - 1));
-                        int a = h1, b = u_v, c = ur ? ur_v : ul_v;
-                        if (by == 0) { a = bx == 0 ? 1024 : h1; b = a; c = a; }
-                        else if (bx == 0) { a = b; c = b; }
-                        const int P = max(min(a, b), min(max(a, b), c));
-                        const int L = decode ? lvl : quant_magic(__dsub_rn(raw, (double)P), st.magic_dc, chroma);   // DPCM_DC_block: D -= P, then quantise
-                        res = L * st.qdc + P;                                                                      // IQuantization + IDPCM_DC_block
-                        *(int2*)(dc2 + 2 * (rowbase + bx)) = make_int2(res, L);
-                    }
-                    h3 = h2; h2 = h1; h1 = res;
-                    raw = raw_n; lvl = lvl_n;
-                }
-                __syncwarp();                               // the next pass reads this pass's last row from shared memory
-            }
+            if (decode && chroma) chain_walk<true, true>(g, slots + base, raw, warp, bw, bh, lane, st.magic_dc, st.qdc);
+            else if (decode) chain_walk<false, true>(g, slots + base, raw, warp, bw, bh, lane, st.magic_dc, st.qdc);
+            else if (chroma) chain_walk<true, false>(g, slots + base, raw, warp, bw, bh, lane, st.magic_dc, st.qdc);
+            else chain_walk<false, false>(g, slots + base, raw, warp, bw, bh, lane, st.magic_dc, st.qdc);
         } else if (warp == 3 && !st.intra && !decode) {
             const int16_t* mv = p.mv + f * g.nmb * 2;
             int16_t* mvd = p.mvd + f * g.nmb * 2;
@@ -309,9 +339,9 @@ __global__ void __launch_bounds__(128) dc_chain_kernel(const __grid_constant__ G
         for (int i6 = threadIdx.x; i6 < nblk; i6 += 128) {
             const int mb = (int)__umulhi((unsigned)i6, 0x2aaaaaabu), k = i6 - 6 * mb;
             if (st.intra && k < 4) continue;
-            const int2 v = *(const int2*)(dc2s + 2 * chain_slot(g, mb, k));
-            rec[i6] = v.x;
-            if (!decode) lvf[i6 * 64] = (int16_t)v.y;
+            const int v = slots[chain_slot(g, mb, k)];
+            rec[i6] = (int)(short)v;
+            if (!decode) lvf[i6 * 64] = (int16_t)(v >> 16);
         }
         return;
     }
@@ -464,12 +494,15 @@ __host__ __device__ inline size_t intra_smem_bytes(const Geom& g)
 
 // `edges` == nullptr: the edge/DC/mode maps live in dynamic shared memory (CIF .. 720x480); otherwise they live in a
 // per-GOP global scratch area of intra_smem_bytes(g) bytes (HD frames; only this CTA touches it, __syncthreads orders it).
-template <int DECODE>
-__global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geom g, FramePtrs p, Step st, unsigned char* edges)
+// THREADS: 96 for batches (8 frames per SM, the throughput configuration); IW_THREADS_WIDE = 192 for small batches, where a
+// frame has an SM to itself and the widest waves (22 blocks) should pass in ONE round of the CTA's 24 block slots instead of two.
+constexpr int IW_THREADS_WIDE = 192;
+template <int DECODE, int THREADS = IW_THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == IW_THREADS ? IW_MIN_CTAS : 2) intra_luma_kernel(Geom g, FramePtrs p, Step st, unsigned char* edges)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ double s_tile[IW_THREADS / 8][72];
-    __shared__ __align__(16) int16_t s_lv[IW_THREADS / 8][72];
+    __shared__ double s_tile[THREADS / 8][72];
+    __shared__ __align__(16) int16_t s_lv[THREADS / 8][72];
     unsigned char* s_raw = edges ? edges + (size_t)blockIdx.x * ((intra_smem_bytes(g) + 15) / 16 * 16) : s_dyn;
     IntraSmem sm;
     sm.dc = (int*)s_raw;
@@ -477,7 +510,7 @@ __global__ void __launch_bounds__(IW_THREADS, IW_MIN_CTAS) intra_luma_kernel(Geo
     sm.right = sm.bot + g.w;
     sm.mode = sm.right + g.h;
     constexpr int TAB = DECODE ? 1 : 0;
-    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7, ngrp = IW_THREADS / 8;
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7, ngrp = THREADS / 8;
     const int gop = blockIdx.x;
     const size_t f = (size_t)gop * st.gop_len + st.t;
     const uint8_t* cury = p.cur + f * g.fb;
@@ -897,6 +930,20 @@ __global__ void __launch_bounds__(32) me_chain_kernel(Geom g, FramePtrs p)
     if (p.meflag[gop] == 0) return;
     if (threadIdx.x != 0) return;
     me_chain_walk(g, p, gop);
+}
+
+// The three fallback passes of one frame in ONE launch (frames that are one segment wide): zero masks, chain walk, re-search.
+// Used after the row-parallel search of small batches, where three more launches would cost more than the search itself.
+__global__ void __launch_bounds__(704) me_fallback_kernel(Geom g, MeLayout L, FramePtrs p, Step st)
+{
+    extern __shared__ __align__(16) unsigned char s_me[];
+    const int gop = blockIdx.x;
+    if (p.meflag[gop] == 0) return;             // natural content: the speculative state-0 search is the answer
+    me_zero_rows(g, L, p, st, gop, 0, s_me);
+    __syncthreads();
+    if (threadIdx.x == 0) me_chain_walk(g, p, gop);
+    __syncthreads();
+    me_search_rows(g, L, p, st, gop, 0, 1, 0, g.mbh, s_me);
 }
 
 // ---- persistent variant of the speculative (state 0) search ------------------------------------------------------

@@ -96,8 +96,11 @@ struct icsp_ctx {
     bool use_graphs = true;                   // ICSP_GRAPHS=0: plain stream launches                   // a CUDA call inside launch bookkeeping failed (event creation, stream join)
     size_t me_smem = 0, me_frame_smem = 0, intra_smem = 0, chain_smem = 0;
     bool me_persistent = true;
+    int intra_wide_max_g = 296;               // up to this many I frames per launch the wavefront kernel runs with 192 threads per frame (ICSP_INTRA_WIDE_G)
+    int me_rows_max_g = 80;                   // up to this many (frame, segment) pairs per launch the search is row-parallel (ICSP_ME_ROWS_G)
     bool me_fused = true;                     // ICSP_ME_FUSED=0: exact carried-state fallback as three separate launches (A/B)
     int chain_staged = 1;
+    float dc_amb_eps = 9.313225746154785e-10f;  // 2^-30, see dc_chain_kernel; ICSP_DC_EPS=1 sends every block down the double path (tests)
     unsigned char* d_intra_edges = nullptr;   // HD frames: per-GOP edge/DC/mode maps of the intra wavefront in global memory
     size_t intra_edge_stride = 0;
     MeLayout me{};
@@ -387,9 +390,13 @@ int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream
     const MeLayout& L = c->me;
     dim3 grid(g.mbh * L.nseg, G);
     const int threads = L.seg_mbs * 32;
-    // one CTA per frame (a frame is one segment): the frame kernel runs the exact fallback itself, no flags to clear, no
-    // further launches
-    const bool fused = c->me_persistent && L.nseg == 1 && c->me_fused;
+    // Big batches: one persistent CTA per frame (a frame is one segment); the frame kernel runs the exact fallback itself, no
+    // flags to clear, no further launches.
+    // Small batches (one 300-frame stream = 30 GOPs per launch): one persistent CTA per frame would leave most SMs idle for the
+    // ~57 us a frame takes, so the rows of a frame are searched by separate CTAs (each restages its own 48-row window) and the
+    // exact fallback follows in one more launch.  Measured on one CIF stream: 39 us instead of 57 us per P frame.
+    const bool persistent = c->me_persistent && (long long)G * L.nseg > c->me_rows_max_g;
+    const bool fused = persistent && L.nseg == 1 && c->me_fused;
     if (!fused) {
         CU(cudaMemsetAsync(p.meflag, 0, sizeof(uint32_t) * G, s));
         CU(cudaMemsetAsync(p.mestate, 0, (size_t)G * g.nmb, s));
@@ -397,13 +404,18 @@ int launch_me(icsp_ctx* c, const FramePtrs& p, const Step& st, int G, cudaStream
     {
         LaunchScope ls(c, K_ME_SAD, s);
         const bool cif = L.pitch_w == 104 && L.seg_mbs == 22;          // CIF: compile-time pitch / segment width
-        if (c->me_persistent && fused && cif) me_sad_frame_kernel<104, 22, true><<<dim3(L.nseg, G), threads, c->me_frame_smem + 16, s>>>(g, L, p, st);
-        else if (c->me_persistent && fused) me_sad_frame_kernel<0, 0, true><<<dim3(L.nseg, G), threads, c->me_frame_smem + 16, s>>>(g, L, p, st);
-        else if (c->me_persistent && cif) me_sad_frame_kernel<104, 22, false><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
-        else if (c->me_persistent) me_sad_frame_kernel<0, 0, false><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
+        if (persistent && fused && cif) me_sad_frame_kernel<104, 22, true><<<dim3(L.nseg, G), threads, c->me_frame_smem + 16, s>>>(g, L, p, st);
+        else if (persistent && fused) me_sad_frame_kernel<0, 0, true><<<dim3(L.nseg, G), threads, c->me_frame_smem + 16, s>>>(g, L, p, st);
+        else if (persistent && cif) me_sad_frame_kernel<104, 22, false><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
+        else if (persistent) me_sad_frame_kernel<0, 0, false><<<dim3(L.nseg, G), threads, c->me_frame_smem, s>>>(g, L, p, st);
         else me_sad_kernel<<<grid, threads, c->me_smem, s>>>(g, L, p, st, 0, 1);
     }
     if (fused) return ICSP_OK;
+    if (L.nseg == 1 && c->me_fused) {
+        LaunchScope ls(c, K_ME_FIXUP, s);
+        me_fallback_kernel<<<G, threads, c->me_smem, s>>>(g, L, p, st);
+        return ICSP_OK;
+    }
     { LaunchScope ls(c, K_ME_ZERO, s); me_zero_kernel<<<dim3(L.nseg, G), threads, c->me_smem, s>>>(g, L, p, st); }
     { LaunchScope ls(c, K_ME_CHAIN, s); me_chain_kernel<<<G, 32, 0, s>>>(g, p); }
     { LaunchScope ls(c, K_ME_FIXUP, s); me_sad_kernel<<<dim3(L.nseg, G), threads, c->me_smem, s>>>(g, L, p, st, 1, g.mbh); }
@@ -426,7 +438,9 @@ int encode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, 
         int hi;
         cudaStream_t h = hi_begin(c, s, hi);
         { LaunchScope ls(c, K_INTRA_ENC, h);
-          intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr); }
+          unsigned char* edges = c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr;
+          if (G <= c->intra_wide_max_g) intra_luma_kernel<0, IW_THREADS_WIDE><<<G, IW_THREADS_WIDE, c->intra_smem, h>>>(g, p, st, edges);
+          else intra_luma_kernel<0><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, edges); }
         hi_end(c, s, hi);
     } else {
         const int rc = launch_me(c, p, st, G, s);
@@ -442,7 +456,7 @@ int encode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, 
     if (!skip_chain) {
         int hi;
         cudaStream_t h = hi_begin(c, s, hi);
-        { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 0, c->chain_staged); }
+        { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 0, c->chain_staged, c->dc_amb_eps); }
         hi_end(c, s, hi);
     }
     stage_done(2);
@@ -499,7 +513,9 @@ int decode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac
             int hi;
             cudaStream_t h = hi_begin(c, s, hi);
             { LaunchScope ls(c, K_INTRA_DEC, h);
-              intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr); }
+              unsigned char* edges = c->d_intra_edges ? c->d_intra_edges + (size_t)g0 * c->intra_edge_stride : nullptr;
+              if (G <= c->intra_wide_max_g) intra_luma_kernel<1, IW_THREADS_WIDE><<<G, IW_THREADS_WIDE, c->intra_smem, h>>>(g, p, st, edges);
+              else intra_luma_kernel<1><<<G, IW_THREADS, c->intra_smem, h>>>(g, p, st, edges); }
             hi_end(c, s, hi);
         } else {
             LaunchScope ls(c, K_MV_RECON, s);
@@ -508,7 +524,7 @@ int decode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac
         {
             int hi;
             cudaStream_t h = hi_begin(c, s, hi);
-            { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 1, c->chain_staged); }
+            { LaunchScope ls(c, K_DCCHAIN, h); dc_chain_kernel<<<G, 128, c->chain_smem, h>>>(g, p, st, 1, c->chain_staged, c->dc_amb_eps); }
             hi_end(c, s, hi);
         }
         {
@@ -679,13 +695,16 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     c->me_smem = me_smem_bytes(c->me);
     c->me_frame_smem = me_frame_smem_bytes(c->me);
     if (const char* e = getenv("ICSP_ME_SMEM_MIN")) c->me_frame_smem = std::max(c->me_frame_smem, (size_t)atoi(e));   // experiments: cap ME CTAs per SM
+    if (const char* e = getenv("ICSP_DC_EPS")) c->dc_amb_eps = (float)atof(e);
     if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
+    if (const char* e = getenv("ICSP_ME_ROWS_G")) c->me_rows_max_g = atoi(e);
+    if (const char* e = getenv("ICSP_INTRA_WIDE_G")) c->intra_wide_max_g = atoi(e);
     if (const char* e = getenv("ICSP_ME_FUSED")) c->me_fused = atoi(e) != 0;
     if (const char* e = getenv("ICSP_TR_V1")) c->tr_v1 = atoi(e) != 0;
     if (const char* e = getenv("ICSP_SKEW")) c->skew = std::max(0, atoi(e));
     if (const char* e = getenv("ICSP_GRAPHS")) c->use_graphs = atoi(e) != 0;
     c->intra_smem = intra_smem_bytes(g);
-    c->chain_smem = (size_t)(6 * g.nmb + 3) * 8 + 32;  // staged: one 8-byte slot per block + a sentinel per plane
+    c->chain_smem = (size_t)(6 * g.nmb + 3) * 4 + 32;  // staged: one 4-byte slot per block
     if (c->chain_smem > 100 * 1024) { c->chain_staged = 0; c->chain_smem = (size_t)6 * g.nmb * sizeof(int) + 32; }
     if (c->intra_smem > 150 * 1024) {   // HD: keep the intra wavefront's maps in global memory (one region per GOP in flight)
         c->intra_edge_stride = (c->intra_smem + 15) / 16 * 16;
@@ -705,6 +724,7 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
         }
         CUB(cudaFuncSetAttribute(me_sad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         CUB(cudaFuncSetAttribute(me_zero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CUB(cudaFuncSetAttribute(me_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         CUB(cudaFuncSetAttribute(me_sad_frame_kernel<104, 22, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         CUB(cudaFuncSetAttribute(me_sad_frame_kernel<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -712,6 +732,8 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
         if ((size_t)optin < c->me_frame_smem + 16) c->me_persistent = false;
         CUB(cudaFuncSetAttribute(intra_luma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
         CUB(cudaFuncSetAttribute(intra_luma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 20 * 1024));
+        CUB(cudaFuncSetAttribute(intra_luma_kernel<0, IW_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 40 * 1024));
+        CUB(cudaFuncSetAttribute(intra_luma_kernel<1, IW_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 40 * 1024));
         CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         // latency-bound kernels want as many resident CTAs as possible: ask for the largest shared-memory carveout
         CUB(cudaFuncSetAttribute(dc_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

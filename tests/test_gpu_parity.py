@@ -502,3 +502,76 @@ def test_cuda_graph_replay_matches_plain_launches(oracle, monkeypatch):
     with IcspCuda(W, H, max_frames=32) as ctx:
         plain = check(ctx)
     assert with_graphs == plain                                # replays are counted like the launches they contain
+
+
+@pytest.mark.parametrize("geom", [(W, H), (64, 48), (1280, 720)])
+def test_dc_chain_integer_path_and_double_path_agree(oracle, monkeypatch, geom):
+    """The DC-DPCM chain codes a block with integer arithmetic unless raw DC + 0.5 is within 2^-30 of an integer, where it falls
+    back to the reference's double sequence (dc_chain_kernel).  Both paths must give the oracle's bits: the default context
+    (integer path for practically every block) and one with ICSP_DC_EPS=1, which sends EVERY block down the double path.  Flat
+    and saturated content puts raw DCs exactly on integers and on k + 0.5 (the ambiguous cases proper)."""
+    from icspcodec_b200 import IcspCuda
+    w, h = geom
+    kinds = ["highmotion", "flat", "akiyo", "saturated"] if (w, h) == (W, H) else ["noise"]
+    for kind in kinds:
+        if kind == "noise":
+            clip = np.random.default_rng(5).integers(0, 256, size=(4, w * h * 3 // 2), dtype=np.uint8)
+        elif kind == "saturated":                   # 8x8 tiles of 0 / 255 that move by one tile per frame: DCs of +-2040, +-1020, 0
+            yy, xx = np.mgrid[0:h * 3 // 2, 0:w]
+            clip = np.stack([(((yy // 8 + xx // 8 + t) & 1) * 255).astype(np.uint8).reshape(-1) for t in range(4)])
+        else:
+            clip = synth.make_clip(kind, 4, 11)
+        for qdc, qac, ip in [(8, 8, 2), (1, 3, 4), (255, 100, 0)]:
+            want = oracle.encode(clip, w, h, qdc, qac, ip)
+            for eps in (None, "1"):
+                if eps is None:
+                    monkeypatch.delenv("ICSP_DC_EPS", raising=False)
+                else:
+                    monkeypatch.setenv("ICSP_DC_EPS", eps)
+                with IcspCuda(w, h, max_frames=8) as ctx:
+                    gop = 1 if ip == 0 else ip
+                    got = ctx.encode_gops(clip, 4 // gop, gop, qdc, qac)
+                    assert_syntax_equal(got, want, what=f"{w}x{h} {kind} qp {qdc}/{qac} ip {ip} eps {eps}: ")
+                    dec = ctx.decode_gops(got.levels, got.mpm, got.ipm, got.mvd, 4 // gop, gop, qdc, qac)
+                    assert np.array_equal(dec, oracle.decode(want, w, h, qdc, qac, max(ip, 1))), f"decode {w}x{h} {kind} qp {qdc}/{qac} ip {ip} eps {eps}"
+
+
+@pytest.mark.parametrize("env", [{"ICSP_ME_ROWS_G": "0"}, {"ICSP_ME_ROWS_G": "1000000"}, {"ICSP_ME_ROWS_G": "0", "ICSP_ME_FUSED": "0"},
+                                 {"ICSP_ME_ROWS_G": "1000000", "ICSP_ME_FUSED": "0"}],
+                         ids=["persistent+fused", "rows+one-fallback-launch", "persistent+3-launches", "rows+3-launches"])
+def test_me_launch_shapes_agree(oracle, monkeypatch, env):
+    """The motion search has two launch shapes — one persistent CTA per frame (big batches) and one CTA per macroblock row
+    (small batches, ICSP_ME_ROWS_G) — and the exact carried-state fallback runs inside the frame kernel, as one more launch, or
+    as three.  Every combination must give the oracle's vectors on clips full of zero-SAD early breaks, also on a frame that is two
+    segments wide (368 = 23 macroblocks) where only the three-launch fallback applies."""
+    from icspcodec_b200 import IcspCuda
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(99)
+    for w, h in ((W, H), (368, 48)):
+        with IcspCuda(w, h, max_frames=12) as ctx:
+            for trial in range(2):
+                clip = _fuzz_clip(rng, 6, w, h)
+                res = ctx.encode_gops(np.concatenate([clip, clip[::-1]]), 2, 6, 8, 8)
+                for i, c in enumerate((clip, clip[::-1])):
+                    s = oracle.encode(np.ascontiguousarray(c), w, h, 8, 8, 6)
+                    sub = type(res)(**{k: (None if getattr(res, k) is None else getattr(res, k)[6 * i:6 * i + 6]) for k in res.__dataclass_fields__})
+                    assert_syntax_equal(sub, s, what=f"{env} {w}x{h} trial {trial} gop {i}: ")
+
+
+@pytest.mark.parametrize("wide_g", ["0", "100000"], ids=["96-thread-frames", "192-thread-frames"])
+def test_intra_wavefront_cta_widths_agree(oracle, monkeypatch, wide_g):
+    """The intra wavefront runs with 96 threads per frame in big batches and with 192 in small ones (ICSP_INTRA_WIDE_G): both
+    widths, encoder and decoder, against the oracle."""
+    from icspcodec_b200 import IcspCuda
+    monkeypatch.setenv("ICSP_INTRA_WIDE_G", wide_g)
+    for (w, h), kind in (((W, H), "highmotion"), ((W, H), "flat"), ((64, 48), None), ((720, 480), None)):
+        clip = synth.make_clip(kind, 4, 3) if kind else np.random.default_rng(8).integers(0, 256, size=(4, w * h * 3 // 2), dtype=np.uint8)
+        with IcspCuda(w, h, max_frames=8) as ctx:
+            for qdc, qac, ip in ((8, 8, 0), (3, 16, 2)):
+                want = oracle.encode(clip, w, h, qdc, qac, ip)
+                gop = 1 if ip == 0 else ip
+                got = ctx.encode_gops(clip, 4 // gop, gop, qdc, qac)
+                assert_syntax_equal(got, want, what=f"{w}x{h} {kind} qp {qdc}/{qac} ip {ip} wide_g {wide_g}: ")
+                dec = ctx.decode_gops(got.levels, got.mpm, got.ipm, got.mvd, 4 // gop, gop, qdc, qac)
+                assert np.array_equal(dec, oracle.decode(want, w, h, qdc, qac, max(ip, 1)))     # the decoder's all-intra is period 1

@@ -20,6 +20,13 @@ with IcspCuda(352, 288, max_frames=8) as ctx:
         offs.append(len(blob)); lens.append(len(b)); blob += b
     out2 = ctx.decode_streams(np.frombuffer(bytes(blob), np.uint8), offs, lens, rows, 2, 1, 4, 8, 8)   # parse_rows_kernel
     assert np.array_equal(out, out2)
+    # round-2 entry points: in-pipeline DCT tap, frame-level shims, stand-alone quantiser, graph replay (second identical call)
+    tap = ctx.encode_gops(frames, 2, 4, 8, 8, with_dct=True)
+    assert np.array_equal(tap.recon, res.recon) and tap.dct is not None
+    ri = ctx.intra_frame(frames[:2], 8, 8, with_dct=True)
+    rp = ctx.inter_frame(frames[1:3], ri.recon, 8, 8)
+    ql = ctx.quant(tap.dct[0].reshape(-1, 64)[:96], 8, 8)
+    assert np.array_equal(ri.recon[0], res.recon[0]) and rp.recon.shape == ri.recon.shape and ql is not None
     print("ok", int(sbits.sum()), out.shape, int(sse.sum()))
 with IcspCuda(64, 48, max_frames=4) as ctx:
     f = np.random.default_rng(0).integers(0, 255, size=(4, 64 * 48 * 3 // 2)).astype(np.uint8)
