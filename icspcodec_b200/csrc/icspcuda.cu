@@ -100,6 +100,7 @@ struct icsp_ctx {
     int me_rows_max_g = 80;                   // up to this many (frame, segment) pairs per launch the search is row-parallel (ICSP_ME_ROWS_G)
     bool me_fused = true;                     // ICSP_ME_FUSED=0: exact carried-state fallback as three separate launches (A/B)
     int chain_staged = 1;
+    bool slice_copies = true;                 // one-chunk host calls: copies sliced by step (ICSP_SLICE_COPIES=0: whole-chunk copies)
     float dc_amb_eps = 9.313225746154785e-10f;  // 2^-30, see dc_chain_kernel; ICSP_DC_EPS=1 sends every block down the double path (tests)
     unsigned char* d_intra_edges = nullptr;   // HD frames: per-GOP edge/DC/mode maps of the intra wavefront in global memory
     size_t intra_edge_stride = 0;
@@ -593,10 +594,13 @@ int entropy_chunk(icsp_ctx* c, int ci, int s0, int ns, int gops_per_stream, int 
 int chunk_gops(const icsp_ctx* c, int n_gops, bool pipelined)
 {
     if (c->chunk_gops_target > 0) return std::min(n_gops, c->chunk_gops_target);
-    const int min_chunk = 148;                       // one intra CTA per SM at least
-    // resident runs: few large chunks (launch overhead, tails); pipelined host calls: more chunks so that the
-    // first upload / last download are short (measured on B200: profiles/README.md)
+    // Measured on B200 (profiles/README.md, chunk sweep): chunks of >= 120 GOPs keep every launch wide enough, and up to four of
+    // them in flight overlap the kernels of different pipes (240 GOPs: 2 x 120 is 9 % faster than one chunk, 480: 4 x 120 is 6 %
+    // faster than 3 x 160, 960: 4 x 240 beats 8 x 120); between 60 and 119 GOPs two half chunks win by 5 % (both halves run the
+    // row-parallel motion search side by side).  Pipelined host calls use up to 8 chunks so that the first upload / last download are short.
+    const int min_chunk = 120;
     int chunks = std::min(pipelined ? 8 : std::max(4, c->n_cstreams), std::max(1, n_gops / min_chunk));
+    if (n_gops >= 60 && n_gops < min_chunk) chunks = 2;
     return (n_gops + chunks - 1) / chunks;
 }
 
@@ -698,6 +702,7 @@ int icsp_create(icsp_ctx** out, int device, int width, int height, int max_frame
     if (const char* e = getenv("ICSP_DC_EPS")) c->dc_amb_eps = (float)atof(e);
     if (const char* e = getenv("ICSP_ME_PERSISTENT")) c->me_persistent = atoi(e) != 0;
     if (const char* e = getenv("ICSP_ME_ROWS_G")) c->me_rows_max_g = atoi(e);
+    if (const char* e = getenv("ICSP_SLICE_COPIES")) c->slice_copies = atoi(e) != 0;
     if (const char* e = getenv("ICSP_INTRA_WIDE_G")) c->intra_wide_max_g = atoi(e);
     if (const char* e = getenv("ICSP_ME_FUSED")) c->me_fused = atoi(e) != 0;
     if (const char* e = getenv("ICSP_TR_V1")) c->tr_v1 = atoi(e) != 0;
@@ -1068,22 +1073,47 @@ static int icsp_encode_streams_impl(icsp_ctx* c, const uint8_t* frames, int n_st
     CU(cudaStreamWaitEvent(c->s_up, c->ev_fork, 0));
     for (int i = 0; i < c->n_cstreams; i++) CU(cudaStreamWaitEvent(c->cstream[i], c->ev_fork, 0));
     CU(cudaStreamWaitEvent(c->s_down, c->ev_fork, 0));
+    const bool sliced = nchunks == 1 && gop_len > 1 && gop_len <= 64 && c->slice_copies;   // one graph and two events per step
     // pass 1: enqueue upload | kernels + entropy | table + recon download for every chunk
     for (int s0 = 0, i = 0; s0 < n_streams; s0 += cs, i++) {
         const int ns = std::min(cs, n_streams - s0);
         const size_t f0 = (size_t)s0 * fps, cnt = (size_t)ns * fps;
         cudaStream_t st = c->cstream[i % c->n_cstreams];
-        CU(cudaMemcpyAsync(c->d_cur + f0 * g.fb, frames + f0 * g.fb, cnt * g.fb, cudaMemcpyHostToDevice, c->s_up));
         cudaEvent_t up = chunk_event(c, 3 * i), done = chunk_event(c, 3 * i + 1), tbl = chunk_event(c, 3 * i + 2);
-        CU(cudaEventRecord(up, c->s_up));
-        CU(cudaStreamWaitEvent(st, up, 0));
-        if ((rc = encode_chunk(c, s0 * gops_per_stream, ns * gops_per_stream, gop_len, qdc, qac, st))) return rc;
+        if (sliced) {
+            // A call that is ONE chunk (a few streams) has nothing to overlap its copies with chunk-wise: upload, 1 ms of kernels
+            // and download would run one after the other.  Its steps are sequential anyway, so the copies are sliced by step
+            // instead: frame t of every GOP is one strided 2-D copy (row = one frame, pitch = one GOP), step t waits for
+            // slice t only, and the reconstruction of step t goes back while step t+1 runs.  One CUDA graph per step.
+            const int G = ns * gops_per_stream, g0 = s0 * gops_per_stream;
+            const size_t pitch = (size_t)gop_len * g.fb;
+            const FramePtrs p = frame_ptrs(c, g0, gop_len);
+            for (int t = 0; t < gop_len; t++) {
+                cudaEvent_t upt = chunk_event(c, 3 * MAX_EN_CHUNKS + 2 * t), dnt = chunk_event(c, 3 * MAX_EN_CHUNKS + 2 * t + 1);
+                CU(cudaMemcpy2DAsync(c->d_cur + (f0 + t) * g.fb, pitch, frames + (f0 + t) * g.fb, pitch, g.fb, (size_t)G, cudaMemcpyHostToDevice, c->s_up));
+                CU(cudaEventRecord(upt, c->s_up));
+                CU(cudaStreamWaitEvent(st, upt, 0));
+                const Step stp = make_step(gop_len, t, qdc, qac);
+                if ((rc = run_captured(c, std::make_tuple(4, g0, G, gop_len, qdc, qac, t), st, [&] { return encode_step(c, p, stp, g0, G, st); }))) return rc;
+                if (out->recon) {
+                    CU(cudaEventRecord(dnt, st));
+                    CU(cudaStreamWaitEvent(c->s_down, dnt, 0));
+                    CU(cudaMemcpy2DAsync(out->recon + (f0 + t) * g.fb, pitch, c->d_rec + (f0 + t) * g.fb, pitch, g.fb, (size_t)G, cudaMemcpyDeviceToHost, c->s_down));
+                }
+            }
+            CU(cudaEventRecord(up, c->s_up));
+        } else {
+            CU(cudaMemcpyAsync(c->d_cur + f0 * g.fb, frames + f0 * g.fb, cnt * g.fb, cudaMemcpyHostToDevice, c->s_up));
+            CU(cudaEventRecord(up, c->s_up));
+            CU(cudaStreamWaitEvent(st, up, 0));
+            if ((rc = encode_chunk(c, s0 * gops_per_stream, ns * gops_per_stream, gop_len, qdc, qac, st))) return rc;
+        }
         if ((rc = entropy_chunk(c, i, s0, ns, gops_per_stream, gop_len, st))) return rc;
         if ((rc = tables_to_host(c, i, st))) return rc;
         CU(cudaEventRecord(done, st));
         CU(cudaEventRecord(tbl, st));
         CU(cudaStreamWaitEvent(c->s_down, done, 0));
-        if (out->recon) CU(cudaMemcpyAsync(out->recon + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, c->s_down));
+        if (out->recon && !sliced) CU(cudaMemcpyAsync(out->recon + f0 * g.fb, c->d_rec + f0 * g.fb, cnt * g.fb, cudaMemcpyDeviceToHost, c->s_down));
         if (timeline) {
             cudaEvent_t e[3];
             for (auto& x : e) cudaEventCreate(&x);

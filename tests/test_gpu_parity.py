@@ -575,3 +575,25 @@ def test_intra_wavefront_cta_widths_agree(oracle, monkeypatch, wide_g):
                 assert_syntax_equal(got, want, what=f"{w}x{h} {kind} qp {qdc}/{qac} ip {ip} wide_g {wide_g}: ")
                 dec = ctx.decode_gops(got.levels, got.mpm, got.ipm, got.mvd, 4 // gop, gop, qdc, qac)
                 assert np.array_equal(dec, oracle.decode(want, w, h, qdc, qac, max(ip, 1)))     # the decoder's all-intra is period 1
+
+
+@pytest.mark.parametrize("slice_copies", ["1", "0"], ids=["copies-sliced-by-step", "whole-chunk-copies"])
+def test_one_chunk_host_call_copy_modes_agree(oracle, monkeypatch, slice_copies):
+    """A host call that is a single chunk uploads / downloads frame t of every GOP as its own strided copy around step t
+    (ICSP_SLICE_COPIES); with the switch off the whole chunk is copied before / after.  Same bits either way, also when the call is
+    repeated (graph replay per step) and for GOP lengths from 2 to 30."""
+    from icspcodec_b200 import IcspCuda, api
+    monkeypatch.setenv("ICSP_SLICE_COPIES", slice_copies)
+    with IcspCuda(W, H, max_frames=64) as ctx:
+        for gop_len, gps, ns in ((3, 2, 3), (30, 1, 2), (2, 5, 1)):
+            n = gop_len * gps
+            clips = [synth.make_clip("highmotion", n, 70 + i) for i in range(ns)]
+            frames = np.concatenate(clips, axis=0)
+            want = [oracle.encode(cl, W, H, 8, 6, gop_len) for cl in clips]
+            for rep in range(2):
+                bodies, sbits, rec = ctx.encode_streams(frames, ns, gps, gop_len, 8, 6, want_recon=True)
+                for i, s in enumerate(want):
+                    assert np.array_equal(rec[i * n:(i + 1) * n], s.recon), f"recon stream {i} gop_len {gop_len} rep {rep}"
+                    ref = oracle.write_bitstream(s, W, H, 8, 6, gop_len)
+                    got = api.finish_stream(bodies[i], int(sbits[i]), W, H, 8, 6, gop_len)
+                    assert got == ref, f"bitstream stream {i} gop_len {gop_len} rep {rep}"
