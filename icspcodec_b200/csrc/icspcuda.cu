@@ -502,12 +502,11 @@ int decode_chunk(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cuda
 {
     return run_captured(c, std::make_tuple(3, g0, G, gop_len, qdc, qac, 0), s, [&] { return decode_chunk_plain(c, g0, G, gop_len, qdc, qac, s); });
 }
-int decode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+// one decoder step (intra-GOP frame index st.t) of GOPs [g0, g0+G) on stream s
+int decode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, cudaStream_t s)
 {
     const Geom& g = c->g;
-    const FramePtrs p = frame_ptrs(c, g0, gop_len);
-    for (int t = 0; t < gop_len; t++) {
-        const Step st = make_step(gop_len, t, qdc, qac);
+    {
         const int per = TR_THREADS / 8;
         dim3 lgrid((g.nmb + per - 1) / per, G);   // one 8-lane group per macroblock
         if (st.intra) {
@@ -534,6 +533,15 @@ int decode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac
             else if (st.intra) idct_recon_kernel2<1, true><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
             else idct_recon_kernel2<1, false><<<lgrid, TR2_THREADS, 0, s>>>(g, p, st);
         }
+    }
+    return ICSP_OK;
+}
+int decode_chunk_plain(icsp_ctx* c, int g0, int G, int gop_len, int qdc, int qac, cudaStream_t s)
+{
+    const FramePtrs p = frame_ptrs(c, g0, gop_len);
+    for (int t = 0; t < gop_len; t++) {
+        const int rc = decode_step(c, p, make_step(gop_len, t, qdc, qac), g0, G, s);
+        if (rc) return rc;
     }
     return ICSP_OK;
 }
@@ -1438,6 +1446,21 @@ static int icsp_decode_streams_impl(icsp_ctx* c, const icsp_dec_bits_in* in, int
             const int n = (int)cnt * g.mbh;
             LaunchScope ls(c, K_PARSE, st);
             parse_rows_kernel<<<(n + 63) / 64, 64, 0, st>>>(g, p, q, gop_len, fps, s0, (int)cnt);
+        }
+        if (n_streams <= cs && gop_len > 1 && gop_len <= 64 && c->slice_copies) {
+            // one chunk: frame t of every GOP goes back while step t+1 runs (see icsp_encode_streams)
+            const int G = ns * gops_per_stream, g0 = s0 * gops_per_stream;
+            const size_t pitch = (size_t)gop_len * g.fb;
+            const FramePtrs p = frame_ptrs(c, g0, gop_len);
+            for (int t = 0; t < gop_len; t++) {
+                const Step stp = make_step(gop_len, t, qdc, qac);
+                if ((rc = run_captured(c, std::make_tuple(5, g0, G, gop_len, qdc, qac, t), st, [&] { return decode_step(c, p, stp, g0, G, st); }))) return rc;
+                cudaEvent_t dnt = chunk_event(c, 2 * MAX_EN_CHUNKS + t);
+                CU(cudaEventRecord(dnt, st));
+                CU(cudaStreamWaitEvent(c->s_down, dnt, 0));
+                CU(cudaMemcpy2DAsync(out + (f0 + t) * g.fb, pitch, c->d_rec + (f0 + t) * g.fb, pitch, g.fb, (size_t)G, cudaMemcpyDeviceToHost, c->s_down));
+            }
+            continue;
         }
         if ((rc = decode_chunk(c, s0 * gops_per_stream, ns * gops_per_stream, gop_len, qdc, qac, st))) return rc;
         CU(cudaEventRecord(done, st));

@@ -597,3 +597,14 @@ def test_one_chunk_host_call_copy_modes_agree(oracle, monkeypatch, slice_copies)
                     ref = oracle.write_bitstream(s, W, H, 8, 6, gop_len)
                     got = api.finish_stream(bodies[i], int(sbits[i]), W, H, 8, 6, gop_len)
                     assert got == ref, f"bitstream stream {i} gop_len {gop_len} rep {rep}"
+                # and back: the GPU bit reader + decoder on the same one-chunk shape (the decoded frames return slice by slice)
+                rows = ctx.bits_row_index(ns * n)
+                blob, offs, lens = bytearray(), [], []
+                for i in range(ns):
+                    body = api.finish_stream(bodies[i], int(sbits[i]), W, H, 8, 6, gop_len)[14:]      # file body without the header
+                    while len(blob) % 4:
+                        blob += b"\x00"
+                    offs.append(len(blob)); lens.append(len(body)); blob += body
+                dec = ctx.decode_streams(np.frombuffer(bytes(blob), np.uint8), offs, lens, rows, ns, gps, gop_len, 8, 6)
+                for i, s in enumerate(want):
+                    assert np.array_equal(dec[i * n:(i + 1) * n], oracle.decode(s, W, H, 8, 6, gop_len)), f"decode stream {i} gop_len {gop_len} rep {rep}"
