@@ -284,6 +284,11 @@ int run_captured(icsp_ctx* c, std::tuple<int, int, int, int, int, int, int> key,
     if (!c->use_graphs || c->profiling || c->d_dct_tap || c->skew) return enqueue();
     auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
+        if (c->graphs.size() >= 1024) {                       // a long-lived context fed ever new shapes: start over instead of growing
+            CU(cudaDeviceSynchronize());
+            for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
+            c->graphs.clear();
+        }
         const uint64_t l0 = c->launches;
         uint64_t c0[K_COUNT];
         for (int k = 0; k < K_COUNT; k++) c0[k] = c->count[k];
