@@ -1204,25 +1204,36 @@ __global__ void __launch_bounds__(256) quant8x8_kernel(const double* in, int32_t
 }
 
 // decoder: motion vector reconstruction mv = mvd + Pm over already reconstructed neighbours (DEC:4301-4370).
-// One warp per frame, waves w = mbx + 2*mby (L, U, UL, UR dependencies).
-__global__ void __launch_bounds__(32) mv_recon_kernel(Geom g, FramePtrs p, Step st)
+// One warp per frame, waves w = mbx + 2*mby (L, U, UL, UR dependencies).  `staged`: the differentials are copied into shared
+// memory first and turned into vectors in place, so that a wave costs a shared-memory round trip instead of a global one
+// (56 dependent waves per CIF frame: 65 -> ~8 us per launch); frames too large for that work on the global array.
+__global__ void __launch_bounds__(32) mv_recon_kernel(Geom g, FramePtrs p, Step st, int staged)
 {
+    extern __shared__ __align__(16) unsigned char s_mvr[];
     const int gop = blockIdx.x, lane = threadIdx.x;
     const size_t f = (size_t)gop * st.gop_len + st.t;
     const int16_t* mvd = p.mvd + f * g.nmb * 2;
     int16_t* mv = p.mv + f * g.nmb * 2;
+    int16_t* w = staged ? (int16_t*)s_mvr : mv;
+    if (staged) {
+        for (int i = lane; i < g.nmb; i += 32) ((int*)w)[i] = ((const int*)mvd)[i];
+        __syncwarp();
+    }
     const int nwaves = (g.mbw - 1) + 2 * (g.mbh - 1) + 1;
     for (int wv = 0; wv < nwaves; wv++) {
         const int lo = max(0, (wv - (g.mbw - 1) + 1) >> 1), hi = min(g.mbh - 1, wv >> 1);
         for (int mby = lo + lane; mby <= hi; mby += 32) {
             const int mb = mby * g.mbw + (wv - 2 * mby);
             int px, py;
-            mv_predictor(mv, g.mbw, mb, px, py);
-            mv[2 * mb] = (int16_t)(mvd[2 * mb] + px);
-            mv[2 * mb + 1] = (int16_t)(mvd[2 * mb + 1] + py);
+            mv_predictor(w, g.mbw, mb, px, py);
+            const int dx = staged ? w[2 * mb] : mvd[2 * mb], dy = staged ? w[2 * mb + 1] : mvd[2 * mb + 1];
+            w[2 * mb] = (int16_t)(dx + px);
+            w[2 * mb + 1] = (int16_t)(dy + py);
         }
         __syncwarp();
     }
+    if (staged)
+        for (int i = lane; i < g.nmb; i += 32) ((int*)mv)[i] = ((const int*)w)[i];
 }
 
 // ---- per-plane sum of squared errors between the source frames and the reconstruction (DEC.h:332-346 computes the luma

@@ -524,7 +524,8 @@ int decode_step(icsp_ctx* c, const FramePtrs& p, const Step& st, int g0, int G, 
             hi_end(c, s, hi);
         } else {
             LaunchScope ls(c, K_MV_RECON, s);
-            mv_recon_kernel<<<G, 32, 0, s>>>(g, p, st);
+            const size_t mv_smem = (size_t)g.nmb * 4 <= 40 * 1024 ? (size_t)g.nmb * 4 : 0;      // vectors of a frame in shared memory (up to 10 240 macroblocks)
+            mv_recon_kernel<<<G, 32, mv_smem, s>>>(g, p, st, mv_smem ? 1 : 0);
         }
         {
             int hi;
